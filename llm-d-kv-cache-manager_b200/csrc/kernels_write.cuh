@@ -1,0 +1,200 @@
+// kernels_write.cuh -- the kvevents.Pool -> Index.Add / Index.Evict write path on the device.
+//
+// Concurrency model: the reference shards messages by FNV-32a(pod) so that one pod's events are
+// applied in arrival order and pods are unordered with respect to each other
+// (pkg/kvcache/kvevents/pool.go:129-144).  Here ONE WARP owns ONE pod's queue and walks it in
+// order; warps of different pods run concurrently and meet only on slot locks.  Within an event
+// the lanes of the warp take the event's blocks in parallel (they are distinct keys), after all
+// lanes have redundantly evaluated the (inherently serial) hash chain.
+#pragma once
+#include "kernels_v1.cuh"
+#include "../../include/kvidx.h"
+
+namespace kvx {
+
+// PodCache.Add under podCache.mu (in_memory.go:199-203) with golang-lru semantics: an existing
+// entry is refreshed to newest, a new one is appended and the oldest dropped beyond the cap.
+__device__ __forceinline__ uint32_t slot_add_entry(ReqSlot* s, uint32_t count, uint16_t pt, uint32_t cap) {
+    volatile uint16_t* e = s->ent;
+    int pos = -1;
+    for (uint32_t j = 0; j < count; ++j) if (e[j] == pt) pos = (int)j;
+    if (pos >= 0) {
+        for (uint32_t j = (uint32_t)pos; j + 1 < count; ++j) e[j] = e[j + 1];
+        e[count - 1] = pt;
+        return count;
+    }
+    if (count >= cap) {
+        for (uint32_t j = 0; j + 1 < count; ++j) e[j] = e[j + 1];
+        --count;
+    }
+    e[count] = pt;
+    return count + 1;
+}
+
+// PodCache.Remove (in_memory.go:233-235): exact (pod,tier) match only.
+__device__ __forceinline__ uint32_t slot_remove_entry(ReqSlot* s, uint32_t count, uint16_t pt) {
+    volatile uint16_t* e = s->ent;
+    for (uint32_t j = 0; j < count; ++j) {
+        if (e[j] == pt) {
+            for (uint32_t q = j; q + 1 < count; ++q) e[q] = e[q + 1];
+            return count - 1;
+        }
+    }
+    return count;
+}
+
+// One (engineKey, requestKey) pair of Index.Add (in_memory.go:159-206).
+__device__ __forceinline__ void do_add(const TableView& t, uint32_t model, uint64_t ehash, uint64_t rhash,
+                                       const uint16_t* __restrict__ pts, int m) {
+    bool created;
+    // 1. engineToRequestKeys.Add(engineKey, requestKey)   (in_memory.go:163)
+    const uint64_t ei = eng_lock(t, model, ehash, false, &created);
+    EngSlot* es = t.eng + ei;
+    *(volatile uint64_t*)&es->rhash = rhash;
+    if (created) atomicAdd(&t.cnt->eng_full, 1ull);
+    eng_unlock(es, make_meta(kStateFull, 0, model));
+    // 2. get-or-create the PodCache and add the entries    (in_memory.go:170-203)
+    const uint64_t ri = req_lock(t, model, rhash, false, &created);
+    ReqSlot* rs = t.req + ri;
+    uint32_t count = created ? 0u : meta_count(ld_volatile_u32(&rs->meta));
+    if (created) atomicAdd(&t.cnt->req_full, 1ull);
+    for (int j = 0; j < m; ++j) count = slot_add_entry(rs, count, pts[j], t.pods_per_key);
+    req_unlock(rs, make_meta(kStateFull, count, model));
+}
+
+// Index.Evict (in_memory.go:212-260).
+__device__ __forceinline__ void do_evict(const TableView& t, uint32_t model, uint64_t ehash,
+                                         const uint16_t* __restrict__ pts, int m) {
+    uint64_t rhash, ei;
+    if (!eng_find(t, model, ehash, &rhash, &ei)) return;                 // :219-223 silent no-op
+    bool created;
+    const uint64_t ri = req_lock(t, model, rhash, true, &created);
+    bool drop_engine = false;
+    if (ri == ~0ull) {
+        drop_engine = true;                                              // :225-230 stale engine mapping
+    } else {
+        ReqSlot* rs = t.req + ri;
+        uint32_t count = meta_count(ld_volatile_u32(&rs->meta));
+        for (int j = 0; j < m; ++j) count = slot_remove_entry(rs, count, pts[j]);
+        if (count == 0) {                                                // :243-256 last entry gone
+            atomicAdd(&t.cnt->req_tomb, 1ull);
+            atomicAdd(&t.cnt->req_full, ~0ull);
+            req_unlock(rs, make_meta(kStateTomb, 0, model));
+            drop_engine = true;
+        } else {
+            req_unlock(rs, make_meta(kStateFull, count, model));
+        }
+    }
+    if (drop_engine) {
+        const uint64_t e2 = eng_lock(t, model, ehash, true, &created);
+        if (e2 != ~0ull) {
+            atomicAdd(&t.cnt->eng_tomb, 1ull);
+            atomicAdd(&t.cnt->eng_full, ~0ull);
+            eng_unlock(t.eng + e2, make_meta(kStateTomb, 0, model));
+        }
+    }
+}
+
+// Index.Add for one call: thread per key pair.
+__global__ void add_kernel(TableView t, uint32_t model, const uint64_t* __restrict__ engine,
+                           const uint64_t* __restrict__ request, int64_t n, const uint16_t* __restrict__ pts, int m) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) do_add(t, model, engine[i], request[i], pts, m);
+}
+
+__global__ void evict_kernel(TableView t, uint32_t model, uint64_t engine, const uint16_t* __restrict__ pts, int m) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) do_evict(t, model, engine, pts, m);
+}
+
+__global__ void get_request_key_kernel(TableView t, uint32_t model, uint64_t engine, uint64_t* out, int* found) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint64_t r = 0;
+        const bool ok = eng_find(t, model, engine, &r);
+        *out = r; *found = ok ? 1 : 0;
+    }
+}
+
+// Pool.digestEvents (kvevents/pool.go:246-338): one warp per pod queue.
+//   ev        events stably sorted by pod; queue q owns ev[queue_off[q] .. queue_off[q+1])
+__global__ void apply_events_kernel(TableView t, const kvidx_event_t* __restrict__ ev, const int64_t* __restrict__ queue_off,
+                                    int64_t n_queues, const uint64_t* __restrict__ hashes, const uint32_t* __restrict__ tokens) {
+    const int lane = threadIdx.x & 31;
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (q >= n_queues) return;
+    const uint32_t B = t.block_size;
+    for (int64_t e = queue_off[q]; e < queue_off[q + 1]; ++e) {
+        const kvidx_event_t evt = ev[e];
+        const uint16_t pt = evt.podtier;
+        if (evt.op == KVIDX_EV_BLOCK_STORED) {
+            // parent request key: GetRequestKey(parent engine key); a miss restarts at the seed (pool.go:279-294)
+            uint64_t h = t.init_hash;
+            if (evt.has_parent) { uint64_t r; if (eng_find(t, evt.model, evt.parent_hash, &r)) h = r; }
+            if (evt.n_hashes == 0) continue;                                 // pool.go:299 `if len(engineKeys) > 0`
+            const uint32_t nblk = evt.n_tokens / B;
+            if (nblk == 0 || nblk != evt.n_hashes) {                         // in_memory.go:150-155 -> event dropped
+                if (lane == 0) atomicAdd(&t.cnt->dropped_events, 1ull);
+                continue;
+            }
+            const uint32_t* tk = tokens + evt.tok_off;
+            const uint64_t* eh = hashes + evt.hash_off;
+            for (uint32_t base = 0; base < nblk; base += 32) {
+                uint64_t mine = 0;
+                const uint32_t lim = min(32u, nblk - base);
+                for (uint32_t j = 0; j < lim; ++j) {                         // every lane walks the chain
+                    h = hash_block_global(h, tk + (size_t)(base + j) * B, B);
+                    if ((uint32_t)lane == j) mine = h;
+                }
+                if ((uint32_t)lane < lim) do_add(t, evt.model, eh[base + lane], mine, &pt, 1);
+                __syncwarp();
+            }
+        } else if (evt.op == KVIDX_EV_BLOCK_REMOVED) {
+            const uint64_t* eh = hashes + evt.hash_off;
+            for (uint32_t base = 0; base < evt.n_hashes; base += 32) {
+                if (base + lane < evt.n_hashes) do_evict(t, evt.model, eh[base + lane], &pt, 1);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Re-insert every FULL slot of an old table into a fresh one (drops tombstones).
+__global__ void rebuild_req_kernel(const ReqSlot* __restrict__ old_tab, uint64_t old_slots, ReqSlot* new_tab, uint64_t new_mask) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= old_slots) return;
+    const uint4* src = reinterpret_cast<const uint4*>(old_tab + i);
+    const uint4 a = src[0], b = src[1];
+    if (meta_state(b.w) != kStateFull) return;
+    const uint64_t tag = ((uint64_t)a.y << 32) | a.x;
+    uint64_t j = home_of(tag, meta_model(b.w)) & new_mask;
+    for (;;) {
+        if (atomicCAS(&new_tab[j].meta, 0u, b.w | kLockBit) == 0u) {
+            uint4* dst = reinterpret_cast<uint4*>(new_tab + j);
+            dst[0] = a;
+            uint32_t* d1 = reinterpret_cast<uint32_t*>(dst + 1);
+            d1[0] = b.x; d1[1] = b.y; d1[2] = b.z;
+            __threadfence();
+            *(volatile uint32_t*)&new_tab[j].meta = b.w & ~kLockBit;
+            return;
+        }
+        j = (j + 1) & new_mask;
+    }
+}
+__global__ void rebuild_eng_kernel(const EngSlot* __restrict__ old_tab, uint64_t old_slots, EngSlot* new_tab, uint64_t new_mask) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= old_slots) return;
+    const EngSlot s = old_tab[i];
+    if (meta_state(s.meta) != kStateFull) return;
+    uint64_t j = home_of(s.ehash, meta_model(s.meta)) & new_mask;
+    for (;;) {
+        if (atomicCAS(&new_tab[j].meta, 0u, s.meta | kLockBit) == 0u) {
+            new_tab[j].ehash = s.ehash; new_tab[j].rhash = s.rhash; new_tab[j].stamp = s.stamp;
+            __threadfence();
+            *(volatile uint32_t*)&new_tab[j].meta = s.meta & ~kLockBit;
+            return;
+        }
+        j = (j + 1) & new_mask;
+    }
+}
+
+}  // namespace kvx

@@ -1,0 +1,684 @@
+// kvidx.cu -- C ABI (include/kvidx.h) over the sm_100a kernels.  No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kvidx.h"
+#include "kernels_v1.cuh"
+#include "kernels_write.cuh"
+#include "kernels_score.cuh"
+
+using namespace kvx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(KVIDX_ECUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+uint64_t pow2ceil(uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; }
+
+// growable device / pinned-host scratch
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t need(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)4096);
+        want = want + want / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t need(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)4096);
+        want = want + want / 4;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+bool is_device_accessible_host(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;     // pinned: cudaMemcpyAsync from it is truly async
+}
+
+}  // namespace
+
+struct kvidx {
+    kvidx_config_t cfg{};
+    TableView tv{};
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    Counters* d_cnt = nullptr;
+    Counters* h_cnt = nullptr;     // pinned mirror
+    uint64_t rebuilds = 0, launches = 0;
+    std::mutex mu;
+    // scratch (guarded by mu)
+    DevBuf d_tok[2], d_off[2], d_model[2], d_filter[2], d_out[2], d_aux[2], d_misc, d_ev, d_hash, d_evtok, d_qoff;
+    PinBuf h_stage[2], h_out[2], h_misc;
+    int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
+};
+
+namespace {
+
+int refresh_counters(kvidx* x) {
+    CK(cudaMemcpyAsync(x->h_cnt, x->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    return 0;
+}
+
+int alloc_tables(kvidx* x, uint64_t req_slots, uint64_t eng_slots, ReqSlot** req, EngSlot** eng) {
+    CK(cudaMalloc((void**)req, req_slots * sizeof(ReqSlot)));
+    CK(cudaMalloc((void**)eng, eng_slots * sizeof(EngSlot)));
+    CK(cudaMemsetAsync(*req, 0, req_slots * sizeof(ReqSlot), x->stream));
+    CK(cudaMemsetAsync(*eng, 0, eng_slots * sizeof(EngSlot), x->stream));
+    return 0;
+}
+
+// Drop tombstones by re-inserting live slots into fresh tables.
+int rebuild(kvidx* x) {
+    const uint64_t rs = x->tv.req_mask + 1, es = x->tv.eng_mask + 1;
+    ReqSlot* nreq; EngSlot* neng;
+    int rc = alloc_tables(x, rs, es, &nreq, &neng);
+    if (rc) return rc;
+    const int T = 256;
+    rebuild_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, rs, nreq, rs - 1);
+    rebuild_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, x->stream>>>(x->tv.eng, es, neng, es - 1);
+    x->launches += 2;
+    CK(cudaGetLastError());
+    // zero the tombstone counters on the device
+    CK(cudaMemsetAsync(&x->d_cnt->req_tomb, 0, sizeof(unsigned long long), x->stream));
+    CK(cudaMemsetAsync(&x->d_cnt->eng_tomb, 0, sizeof(unsigned long long), x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    cudaFree(x->tv.req); cudaFree(x->tv.eng);
+    x->tv.req = nreq; x->tv.eng = neng;
+    ++x->rebuilds;
+    return refresh_counters(x);
+}
+
+// Make room for up to `incoming` new keys in each table before a write batch.
+int ensure_room(kvidx* x, uint64_t incoming) {
+    const uint64_t rs = x->tv.req_mask + 1, es = x->tv.eng_mask + 1;
+    auto over = [&](uint64_t full, uint64_t tomb, uint64_t slots) { return (full + tomb + incoming) * 10 > slots * 8; };
+    const Counters& c = *x->h_cnt;
+    if (over(c.req_full, c.req_tomb, rs) || over(c.eng_full, c.eng_tomb, es)) {
+        if (c.req_tomb || c.eng_tomb) { int rc = rebuild(x); if (rc) return rc; }
+        const Counters& d = *x->h_cnt;
+        if ((d.req_full + incoming) * 10 > rs * 9 || (d.eng_full + incoming) * 10 > es * 9)
+            return fail(KVIDX_ENOSPC, "table full: %llu request keys + %llu incoming in %llu slots",
+                        (unsigned long long)d.req_full, (unsigned long long)incoming, (unsigned long long)rs);
+    }
+    return 0;
+}
+
+struct ScoreOut { double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* sp_cnt; uint8_t* has_keys; };
+
+// Launch the score kernel over device-resident inputs.
+int launch_score(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
+                 const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (x->score_kernel == 1) {
+        const int T = 128;
+        score_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
+                                                                  o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys);
+        x->launches += 1;
+    } else {
+        int rc = launch_score_tuned(x->tv, x->sm_count, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
+                                    o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, &x->d_cnt->pad, st, &x->launches);
+        if (rc) return fail(KVIDX_ECUDA, "score launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int check_csr(const int64_t* off, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) if (off[i + 1] < off[i]) return fail(KVIDX_EINVAL, "tok_off not monotone at %lld", (long long)i);
+    return 0;
+}
+
+// Host-buffer scoring: chunks of prompts are staged through two pinned slots so that the copy of
+// chunk c+1 overlaps the kernel of chunk c and the read-back of chunk c-1.
+int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
+               const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys) {
+    if (n < 0 || !tok_off) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    int rc = check_csr(tok_off, n);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    const uint32_t P = x->tv.max_pods, FW = x->tv.filter_words;
+    const bool sparse = sp_cnt != nullptr;
+    const size_t out_row = sparse ? (size_t)kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 1 : (size_t)P * sizeof(double);
+    // chunking: bound staged tokens to ~64 MiB and output to ~64 MiB per slot
+    const int64_t kMaxTokChunk = 16ll << 20;      // tokens
+    const int64_t kMaxRowsChunk = std::max<int64_t>(1, (64ll << 20) / (int64_t)out_row);
+    const bool tok_pinned = is_device_accessible_host(tok);
+    int64_t i0 = 0;
+    int slot = 0;
+    struct Pending { bool live = false; int64_t i0 = 0, cnt = 0; } pend[2];
+    auto drain = [&](int s) -> int {
+        if (!pend[s].live) return 0;
+        CK(cudaEventSynchronize(x->ev_done[s]));
+        const int64_t c = pend[s].cnt, b = pend[s].i0;
+        const uint8_t* ho = x->h_out[s].as<uint8_t>();
+        if (!sparse) {
+            memcpy(dense + b * (int64_t)P, ho, (size_t)c * P * sizeof(double));
+            if (has_keys) memcpy(has_keys + b, ho + (size_t)c * P * sizeof(double), (size_t)c);
+        } else {
+            size_t o = 0;
+            memcpy(sp_scores + b * kMaxEnt, ho + o, (size_t)c * kMaxEnt * sizeof(double)); o += (size_t)c * kMaxEnt * sizeof(double);
+            memcpy(sp_pods + b * kMaxEnt, ho + o, (size_t)c * kMaxEnt * sizeof(uint16_t)); o += (size_t)c * kMaxEnt * sizeof(uint16_t);
+            memcpy(sp_cnt + b, ho + o, (size_t)c); o += (size_t)c;
+            if (has_keys) memcpy(has_keys + b, ho + o, (size_t)c);
+        }
+        pend[s].live = false;
+        return 0;
+    };
+    while (i0 < n) {
+        int64_t i1 = i0;
+        while (i1 < n && (i1 - i0) < kMaxRowsChunk && (tok_off[i1 + 1] - tok_off[i0]) <= kMaxTokChunk) ++i1;
+        if (i1 == i0) i1 = i0 + 1;    // a single prompt larger than the chunk budget
+        const int64_t c = i1 - i0, tb = tok_off[i0], nt = tok_off[i1] - tb;
+        rc = drain(slot);
+        if (rc) return rc;
+        // stage
+        CK(x->d_tok[slot].need((size_t)std::max<int64_t>(nt, 1) * 4 + 64));
+        CK(x->d_off[slot].need((size_t)(c + 1) * 8));
+        const uint32_t* src = tok + tb;
+        size_t stage_bytes = (size_t)(c + 1) * 8 + (model ? (size_t)c * 4 : 0) + (filter ? (size_t)c * FW * 8 : 0) + (tok_pinned ? 0 : (size_t)nt * 4);
+        CK(x->h_stage[slot].need(stage_bytes + 64));
+        uint8_t* hs = x->h_stage[slot].as<uint8_t>();
+        size_t o = 0;
+        memcpy(hs + o, tok_off + i0, (size_t)(c + 1) * 8);
+        CK(cudaMemcpyAsync(x->d_off[slot].p, hs + o, (size_t)(c + 1) * 8, cudaMemcpyHostToDevice, x->stream)); o += (size_t)(c + 1) * 8;
+        const uint32_t* dm = nullptr; const uint64_t* df = nullptr;
+        if (model) {
+            CK(x->d_model[slot].need((size_t)c * 4));
+            memcpy(hs + o, model + i0, (size_t)c * 4);
+            CK(cudaMemcpyAsync(x->d_model[slot].p, hs + o, (size_t)c * 4, cudaMemcpyHostToDevice, x->stream)); o += (size_t)c * 4;
+            dm = x->d_model[slot].as<uint32_t>();
+        }
+        if (filter) {
+            CK(x->d_filter[slot].need((size_t)c * FW * 8));
+            memcpy(hs + o, filter + i0 * FW, (size_t)c * FW * 8);
+            CK(cudaMemcpyAsync(x->d_filter[slot].p, hs + o, (size_t)c * FW * 8, cudaMemcpyHostToDevice, x->stream)); o += (size_t)c * FW * 8;
+            df = x->d_filter[slot].as<uint64_t>();
+        }
+        if (nt > 0) {
+            if (tok_pinned) {
+                CK(cudaMemcpyAsync(x->d_tok[slot].p, src, (size_t)nt * 4, cudaMemcpyHostToDevice, x->stream));
+            } else {
+                memcpy(hs + o, src, (size_t)nt * 4);
+                CK(cudaMemcpyAsync(x->d_tok[slot].p, hs + o, (size_t)nt * 4, cudaMemcpyHostToDevice, x->stream));
+            }
+        }
+        // outputs
+        CK(x->d_out[slot].need((size_t)c * out_row + (size_t)c + 64));
+        CK(x->h_out[slot].need((size_t)c * out_row + (size_t)c + 64));
+        uint8_t* dout = x->d_out[slot].as<uint8_t>();
+        ScoreOut so{};
+        size_t total;
+        if (!sparse) {
+            so.dense = reinterpret_cast<double*>(dout);
+            so.has_keys = dout + (size_t)c * P * sizeof(double);
+            total = (size_t)c * P * sizeof(double) + (size_t)c;
+        } else {
+            size_t q = 0;
+            so.sp_scores = reinterpret_cast<double*>(dout + q); q += (size_t)c * kMaxEnt * sizeof(double);
+            so.sp_pods = reinterpret_cast<uint16_t*>(dout + q); q += (size_t)c * kMaxEnt * sizeof(uint16_t);
+            so.sp_cnt = dout + q; q += (size_t)c;
+            so.has_keys = dout + q; q += (size_t)c;
+            total = q;
+        }
+        rc = launch_score(x, x->d_tok[slot].as<uint32_t>(), x->d_off[slot].as<int64_t>(), tb, c, dm, model0, df, so, x->stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(x->h_out[slot].p, dout, total, cudaMemcpyDeviceToHost, x->stream));
+        CK(cudaEventRecord(x->ev_done[slot], x->stream));
+        pend[slot].live = true; pend[slot].i0 = i0; pend[slot].cnt = c;
+        slot ^= 1;
+        i0 = i1;
+    }
+    rc = drain(slot); if (rc) return rc;
+    rc = drain(slot ^ 1); if (rc) return rc;
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int kvidx_abi_version(void) { return KVIDX_ABI_VERSION; }
+
+void kvidx_config_default(kvidx_config_t* c) {
+    if (!c) return;
+    memset(c, 0, sizeof *c);
+    c->struct_size = sizeof *c;
+    c->device = 0;
+    c->block_size = 16;                      // token_processor.go:31
+    c->pods_per_key = KVIDX_MAX_PODS_PER_KEY; // in_memory.go:34
+    c->init_hash = kFnvOffset;               // FNV64a("")  (HashSeed default "", token_processor.go:48)
+    c->capacity = 1ull << 20;
+    c->table_slots = 0;
+    c->max_pods = 256;
+    c->n_tier_weights = 2;
+    for (auto& w : c->tier_weight) w = 1.0;
+    c->tier_weight[0] = 1.0;                 // "gpu"  backend.go:28
+    c->tier_weight[1] = 0.8;                 // "cpu"  backend.go:29
+    c->lru_exact = 0;
+}
+
+const char* kvidx_last_error(kvidx_t*) { return g_err.c_str(); }
+
+uint64_t kvidx_fnv64a(const void* data, size_t n) {
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    uint64_t h = kFnvOffset;
+    for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * kFnvPrime;
+    return h;
+}
+uint32_t kvidx_fnv32a(const void* data, size_t n) {
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    uint32_t h = 0x811C9DC5u;
+    for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 0x01000193u;
+    return h;
+}
+uint32_t kvidx_queue_index(const char* pod, size_t n, uint32_t concurrency) {
+    return concurrency ? kvidx_fnv32a(pod, n) % concurrency : 0;
+}
+
+void* kvidx_host_alloc(size_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void kvidx_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
+    if (!out) return fail(KVIDX_EINVAL, "out is NULL");
+    *out = nullptr;
+    kvidx_config_t c;
+    kvidx_config_default(&c);
+    if (cfg_in) {
+        if (cfg_in->struct_size == 0 || cfg_in->struct_size > sizeof c) return fail(KVIDX_EINVAL, "bad struct_size");
+        memcpy(&c, cfg_in, cfg_in->struct_size);
+        c.struct_size = sizeof c;
+    }
+    if (c.block_size == 0) c.block_size = 16;
+    if (c.pods_per_key == 0) c.pods_per_key = KVIDX_MAX_PODS_PER_KEY;
+    if (c.pods_per_key > KVIDX_MAX_PODS_PER_KEY) return fail(KVIDX_EINVAL, "pods_per_key %u > %d", c.pods_per_key, KVIDX_MAX_PODS_PER_KEY);
+    if (c.capacity == 0) c.capacity = 1ull << 20;
+    if (c.max_pods == 0) c.max_pods = 256;
+    if (c.max_pods > KVIDX_MAX_PODS) return fail(KVIDX_ERANGE, "max_pods %u > %u", c.max_pods, KVIDX_MAX_PODS);
+    if (c.n_tier_weights > KVIDX_MAX_TIERS) return fail(KVIDX_ERANGE, "n_tier_weights > 16");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(KVIDX_ECUDA, "no CUDA device: libkvidx has no CPU fallback");
+    }
+    if (c.device < 0 || c.device >= ndev) return fail(KVIDX_EINVAL, "device %d out of range (%d devices)", c.device, ndev);
+    CK(cudaSetDevice(c.device));
+    kvidx* x = new kvidx();
+    x->cfg = c;
+    x->device = c.device;
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    x->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) { delete x; return fail(KVIDX_ECUDA, "device sm_%d%d is not Blackwell; libkvidx is built for sm_100a only", prop.major, prop.minor); }
+    CK(cudaStreamCreateWithFlags(&x->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+    x->stream = x->own_stream;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&x->ev_done[i], cudaEventDisableTiming));
+    }
+    uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(2 * c.capacity, 1024));
+    if (slots < 1024) slots = 1024;
+    TableView& t = x->tv;
+    t.req_mask = slots - 1; t.eng_mask = slots - 1;
+    t.capacity = c.capacity; t.init_hash = c.init_hash; t.block_size = c.block_size; t.pods_per_key = c.pods_per_key;
+    t.max_pods = c.max_pods; t.filter_words = (c.max_pods + 63) / 64;
+    for (int i = 0; i < 16; ++i) t.weight[i] = (uint32_t)i < c.n_tier_weights ? c.tier_weight[i] : 1.0;
+    t.req_stamp = nullptr;
+    int rc = alloc_tables(x, slots, slots, &t.req, &t.eng);
+    if (rc) { delete x; return rc; }
+    CK(cudaMalloc((void**)&x->d_cnt, sizeof(Counters)));
+    CK(cudaMemsetAsync(x->d_cnt, 0, sizeof(Counters), x->stream));
+    CK(cudaMallocHost((void**)&x->h_cnt, sizeof(Counters)));
+    memset(x->h_cnt, 0, sizeof(Counters));
+    t.cnt = x->d_cnt;
+    CK(cudaStreamSynchronize(x->stream));
+    if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
+    rc = score_tuned_init();
+    if (rc) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    *out = x;
+    return 0;
+}
+
+void kvidx_destroy(kvidx_t* x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        x->d_tok[i].release(); x->d_off[i].release(); x->d_model[i].release(); x->d_filter[i].release();
+        x->d_out[i].release(); x->d_aux[i].release(); x->h_stage[i].release(); x->h_out[i].release();
+        if (x->ev_h2d[i]) cudaEventDestroy(x->ev_h2d[i]);
+        if (x->ev_done[i]) cudaEventDestroy(x->ev_done[i]);
+    }
+    x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
+    if (x->tv.req) cudaFree(x->tv.req);
+    if (x->tv.eng) cudaFree(x->tv.eng);
+    if (x->tv.req_stamp) cudaFree(x->tv.req_stamp);
+    if (x->d_cnt) cudaFree(x->d_cnt);
+    if (x->h_cnt) cudaFreeHost(x->h_cnt);
+    if (x->own_stream) cudaStreamDestroy(x->own_stream);
+    if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
+    delete x;
+}
+
+int kvidx_set_tier_weight(kvidx_t* x, uint32_t tier, double w) {
+    if (!x) return fail(KVIDX_EINVAL, "NULL handle");
+    if (tier >= KVIDX_MAX_TIERS) return fail(KVIDX_ERANGE, "tier %u out of range", tier);
+    std::lock_guard<std::mutex> g(x->mu);
+    x->tv.weight[tier] = w;
+    return 0;
+}
+
+int kvidx_set_stream(kvidx_t* x, void* s) {
+    if (!x) return fail(KVIDX_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> g(x->mu);
+    x->stream = s ? static_cast<cudaStream_t>(s) : x->own_stream;
+    return 0;
+}
+int kvidx_synchronize(kvidx_t* x) {
+    if (!x) return fail(KVIDX_EINVAL, "NULL handle");
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamSynchronize(x->stream));
+    return 0;
+}
+
+// ---- read path ------------------------------------------------------------------------------
+
+int kvidx_hash_keys(kvidx_t* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint64_t* parent,
+                    const uint8_t* parent_valid, uint64_t* keys_out, int64_t* key_off_out) {
+    if (!x || !tok_off || !key_off_out || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    int rc = check_csr(tok_off, n);
+    if (rc) return rc;
+    const uint32_t B = x->tv.block_size;
+    int64_t nk = 0;
+    for (int64_t i = 0; i < n; ++i) { key_off_out[i] = nk; nk += (tok_off[i + 1] - tok_off[i]) / B; }
+    key_off_out[n] = nk;
+    if (n == 0 || nk == 0) return 0;
+    if (!keys_out || !tok) return fail(KVIDX_EINVAL, "NULL buffer");
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    const int64_t tb = tok_off[0], nt = tok_off[n] - tb;
+    CK(x->d_tok[0].need((size_t)nt * 4 + 64));
+    CK(x->d_off[0].need((size_t)(n + 1) * 8));
+    CK(x->d_aux[0].need((size_t)(n + 1) * 8 + (size_t)n * 9));
+    CK(x->d_out[0].need((size_t)nk * 8));
+    CK(cudaMemcpyAsync(x->d_tok[0].p, tok + tb, (size_t)nt * 4, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(x->d_off[0].p, tok_off, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, x->stream));
+    uint8_t* aux = x->d_aux[0].as<uint8_t>();
+    int64_t* d_koff = reinterpret_cast<int64_t*>(aux);
+    uint64_t* d_parent = nullptr; uint8_t* d_pv = nullptr;
+    CK(cudaMemcpyAsync(d_koff, key_off_out, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, x->stream));
+    if (parent) {
+        d_parent = reinterpret_cast<uint64_t*>(aux + (size_t)(n + 1) * 8);
+        CK(cudaMemcpyAsync(d_parent, parent, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
+        if (parent_valid) {
+            d_pv = aux + (size_t)(n + 1) * 8 + (size_t)n * 8;
+            CK(cudaMemcpyAsync(d_pv, parent_valid, (size_t)n, cudaMemcpyHostToDevice, x->stream));
+        }
+    }
+    const int T = 128;
+    hash_keys_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, x->d_tok[0].as<uint32_t>(), x->d_off[0].as<int64_t>(), tb, n,
+                                                                         d_parent, d_pv, d_koff, 0, x->d_out[0].as<uint64_t>());
+    x->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(keys_out, x->d_out[0].p, (size_t)nk * 8, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    return 0;
+}
+
+int kvidx_hash_keys_dev(kvidx_t* x, const uint32_t* d_tok, const int64_t* d_tok_off, int64_t n, const uint64_t* d_parent,
+                        const uint8_t* d_parent_valid, const int64_t* d_key_off, uint64_t* d_keys_out) {
+    if (!x || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    const int T = 128;
+    hash_keys_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, d_tok, d_tok_off, 0, n, d_parent, d_parent_valid, d_key_off, 0, d_keys_out);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int kvidx_lookup(kvidx_t* x, uint32_t model, const uint64_t* keys, int64_t n, const uint64_t* filter,
+                 kvidx_podtier_t* podtier_out, uint8_t* cnt_out) {
+    if (!x) return fail(KVIDX_EINVAL, "NULL handle");
+    if (n <= 0 || !keys) return fail(KVIDX_EINVAL, "no requestKeys provided for lookup");   // in_memory.go:108-110
+    if (!podtier_out || !cnt_out) return fail(KVIDX_EINVAL, "NULL output");
+    if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    const uint32_t FW = x->tv.filter_words;
+    CK(x->d_aux[0].need((size_t)n * 8 + (size_t)FW * 8 + 16));
+    CK(x->d_out[0].need((size_t)n * kMaxEnt * 2 + (size_t)n + 16));
+    uint8_t* aux = x->d_aux[0].as<uint8_t>();
+    uint64_t* d_keys = reinterpret_cast<uint64_t*>(aux);
+    uint64_t* d_f = nullptr;
+    int* d_cut = reinterpret_cast<int*>(aux + (size_t)n * 8 + (size_t)FW * 8);
+    CK(cudaMemcpyAsync(d_keys, keys, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
+    if (filter) {
+        d_f = reinterpret_cast<uint64_t*>(aux + (size_t)n * 8);
+        CK(cudaMemcpyAsync(d_f, filter, (size_t)FW * 8, cudaMemcpyHostToDevice, x->stream));
+    }
+    const int big = 0x7fffffff;
+    CK(cudaMemcpyAsync(d_cut, &big, sizeof(int), cudaMemcpyHostToDevice, x->stream));
+    uint16_t* d_pt = x->d_out[0].as<uint16_t>();
+    uint8_t* d_cnt = x->d_out[0].as<uint8_t>() + (size_t)n * kMaxEnt * 2;
+    const int T = 128;
+    lookup_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, model, d_keys, n, d_f, d_pt, d_cnt, d_cut);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    int cut = big;
+    CK(cudaMemcpyAsync(podtier_out, d_pt, (size_t)n * kMaxEnt * 2, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(cnt_out, d_cnt, (size_t)n, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(&cut, d_cut, sizeof(int), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    if (cut != big) for (int64_t i = cut; i < n; ++i) cnt_out[i] = 0;   // in_memory.go:119-122 early return
+    return 0;
+}
+
+int kvidx_score_batch(kvidx_t* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
+                      const uint64_t* filter, double* scores_out, uint8_t* has_keys_out) {
+    if (!x || !scores_out) return fail(KVIDX_EINVAL, "bad arguments");
+    return score_host(x, tok, tok_off, n, model, model0, filter, scores_out, nullptr, nullptr, nullptr, has_keys_out);
+}
+
+int kvidx_score_batch_sparse(kvidx_t* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
+                             const uint64_t* filter, uint16_t* pods_out, double* scores_out, uint8_t* cnt_out, uint8_t* has_keys_out) {
+    if (!x || !pods_out || !scores_out || !cnt_out) return fail(KVIDX_EINVAL, "bad arguments");
+    return score_host(x, tok, tok_off, n, model, model0, filter, nullptr, pods_out, scores_out, cnt_out, has_keys_out);
+}
+
+int kvidx_score_batch_dev(kvidx_t* x, const uint32_t* d_tok, const int64_t* d_tok_off, int64_t n, const uint32_t* d_model,
+                          uint32_t model0, const uint64_t* d_filter, double* d_scores_out, uint8_t* d_has_keys_out) {
+    if (!x || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    ScoreOut so{};
+    so.dense = d_scores_out; so.has_keys = d_has_keys_out;
+    return launch_score(x, d_tok, d_tok_off, 0, n, d_model, model0, d_filter, so, x->stream);
+}
+
+// ---- write path -----------------------------------------------------------------------------
+
+int kvidx_add(kvidx_t* x, uint32_t model, const uint64_t* engine, const uint64_t* request, int64_t n,
+              const kvidx_podtier_t* pts, int32_t m) {
+    if (!x) return fail(KVIDX_EINVAL, "NULL handle");
+    if (n <= 0 || m <= 0 || !engine || !request || !pts) return fail(KVIDX_EINVAL, "no keys or entries provided for adding to index");
+    if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    int rc = ensure_room(x, (uint64_t)n);
+    if (rc) return rc;
+    CK(x->d_misc.need((size_t)n * 16 + (size_t)m * 2 + 16));
+    uint8_t* d = x->d_misc.as<uint8_t>();
+    CK(cudaMemcpyAsync(d, engine, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(d + (size_t)n * 8, request, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(d + (size_t)n * 16, pts, (size_t)m * 2, cudaMemcpyHostToDevice, x->stream));
+    const int T = 128;
+    add_kernel<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, model, reinterpret_cast<uint64_t*>(d),
+                                                                reinterpret_cast<uint64_t*>(d + (size_t)n * 8), n,
+                                                                reinterpret_cast<uint16_t*>(d + (size_t)n * 16), m);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return refresh_counters(x);
+}
+
+int kvidx_evict(kvidx_t* x, uint32_t model, uint64_t engine, const kvidx_podtier_t* pts, int32_t m) {
+    if (!x) return fail(KVIDX_EINVAL, "NULL handle");
+    if (m <= 0 || !pts) return fail(KVIDX_EINVAL, "no entries provided for eviction from index");
+    if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    CK(x->d_misc.need((size_t)m * 2 + 16));
+    CK(cudaMemcpyAsync(x->d_misc.p, pts, (size_t)m * 2, cudaMemcpyHostToDevice, x->stream));
+    evict_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, x->d_misc.as<uint16_t>(), m);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return refresh_counters(x);
+}
+
+int kvidx_get_request_key(kvidx_t* x, uint32_t model, uint64_t engine, uint64_t* out) {
+    if (!x || !out) return fail(KVIDX_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    CK(x->d_misc.need(32));
+    uint64_t* d_out = x->d_misc.as<uint64_t>();
+    int* d_found = reinterpret_cast<int*>(d_out + 1);
+    get_request_key_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, d_out, d_found);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    struct { uint64_t r; int f; int pad; } h{};
+    CK(cudaMemcpyAsync(&h, d_out, 16, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    if (!h.f) return fail(KVIDX_ENOENT, "engine key not found: %u@%llu", model, (unsigned long long)engine);
+    *out = h.r;
+    return 0;
+}
+
+int kvidx_apply_events_dev(kvidx_t* x, const kvidx_event_t* d_ev_sorted, const int64_t* d_queue_off, int64_t n_queues,
+                           const uint64_t* d_hashes, const uint32_t* d_tokens, int64_t* d_n_dropped) {
+    if (!x || n_queues < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n_queues == 0) return 0;
+    (void)d_n_dropped;
+    CK(cudaSetDevice(x->device));
+    const int T = 128;   // 4 queues per CTA
+    const int64_t warps = n_queues;
+    apply_events_kernel<<<(unsigned)((warps * 32 + T - 1) / T), T, 0, x->stream>>>(x->tv, d_ev_sorted, d_queue_off, n_queues, d_hashes, d_tokens);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int kvidx_apply_events(kvidx_t* x, const kvidx_event_t* ev, int64_t n, const uint64_t* hashes, int64_t n_hashes,
+                       const uint32_t* tokens, int64_t n_tokens, int64_t* n_dropped_out) {
+    if (!x || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n_dropped_out) *n_dropped_out = 0;
+    if (n == 0) return 0;
+    if (!ev) return fail(KVIDX_EINVAL, "NULL events");
+    // validate + stable counting sort by pod -> per-pod FIFO queues (pool.go:129-144)
+    std::vector<int64_t> qcount(KVIDX_MAX_PODS + 1, 0);
+    uint64_t new_keys = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const kvidx_event_t& e = ev[i];
+        if (e.op > KVIDX_EV_BLOCK_REMOVED) return fail(KVIDX_EINVAL, "event %lld: unknown op %u", (long long)i, e.op);
+        if (e.model > 0xffffu) return fail(KVIDX_ERANGE, "event %lld: model id %u > 65535", (long long)i, e.model);
+        if (e.hash_off + e.n_hashes > (uint64_t)n_hashes) return fail(KVIDX_EINVAL, "event %lld: hashes out of range", (long long)i);
+        if (e.op == KVIDX_EV_BLOCK_STORED) {
+            if (e.tok_off + e.n_tokens > (uint64_t)n_tokens) return fail(KVIDX_EINVAL, "event %lld: tokens out of range", (long long)i);
+            new_keys += e.n_hashes;
+        }
+        qcount[KVIDX_PT_POD(e.podtier) + 1]++;
+    }
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    int rc = ensure_room(x, new_keys);
+    if (rc) return rc;
+    // compact non-empty queues
+    std::vector<int64_t> start(KVIDX_MAX_PODS + 1, 0);
+    for (uint32_t p = 0; p < KVIDX_MAX_PODS; ++p) start[p + 1] = start[p] + qcount[p + 1];
+    CK(x->h_misc.need((size_t)n * sizeof(kvidx_event_t) + (size_t)(KVIDX_MAX_PODS + 2) * 8));
+    kvidx_event_t* sorted = x->h_misc.as<kvidx_event_t>();
+    int64_t* qoff = reinterpret_cast<int64_t*>(x->h_misc.as<uint8_t>() + (size_t)n * sizeof(kvidx_event_t));
+    {
+        std::vector<int64_t> cur(start.begin(), start.end() - 1);
+        for (int64_t i = 0; i < n; ++i) sorted[cur[KVIDX_PT_POD(ev[i].podtier)]++] = ev[i];
+    }
+    int64_t nq = 0;
+    for (uint32_t p = 0; p < KVIDX_MAX_PODS; ++p) if (qcount[p + 1]) { qoff[nq++] = start[p]; }
+    qoff[nq] = n;
+    CK(x->d_ev.need((size_t)n * sizeof(kvidx_event_t)));
+    CK(x->d_qoff.need((size_t)(nq + 1) * 8));
+    CK(x->d_hash.need((size_t)std::max<int64_t>(n_hashes, 1) * 8));
+    CK(x->d_evtok.need((size_t)std::max<int64_t>(n_tokens, 1) * 4));
+    CK(cudaMemcpyAsync(x->d_ev.p, sorted, (size_t)n * sizeof(kvidx_event_t), cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(x->d_qoff.p, qoff, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, x->stream));
+    if (n_hashes > 0) CK(cudaMemcpyAsync(x->d_hash.p, hashes, (size_t)n_hashes * 8, cudaMemcpyHostToDevice, x->stream));
+    if (n_tokens > 0) CK(cudaMemcpyAsync(x->d_evtok.p, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, x->stream));
+    const unsigned long long dropped_before = x->h_cnt->dropped_events;
+    rc = kvidx_apply_events_dev(x, x->d_ev.as<kvidx_event_t>(), x->d_qoff.as<int64_t>(), nq, x->d_hash.as<uint64_t>(),
+                                x->d_evtok.as<uint32_t>(), nullptr);
+    if (rc) return rc;
+    rc = refresh_counters(x);
+    if (rc) return rc;
+    if (n_dropped_out) *n_dropped_out = (int64_t)(x->h_cnt->dropped_events - dropped_before);
+    return 0;
+}
+
+int kvidx_get_stats(kvidx_t* x, kvidx_stats_t* out) {
+    if (!x || !out) return fail(KVIDX_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    int rc = refresh_counters(x);
+    if (rc) return rc;
+    out->request_keys = x->h_cnt->req_full; out->engine_keys = x->h_cnt->eng_full;
+    out->request_tombs = x->h_cnt->req_tomb; out->engine_tombs = x->h_cnt->eng_tomb;
+    out->request_slots = x->tv.req_mask + 1; out->engine_slots = x->tv.eng_mask + 1;
+    out->rebuilds = x->rebuilds; out->kernel_launches = x->launches;
+    return 0;
+}
+
+}  // extern "C"
