@@ -81,8 +81,8 @@ struct kvidx {
     TableView tv{};
     int device = 0;
     int sm_count = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
     Counters* d_cnt = nullptr;
     Counters* h_cnt = nullptr;     // pinned mirror
     uint64_t rebuilds = 0, launches = 0;
@@ -170,29 +170,35 @@ int check_csr(const int64_t* off, int64_t n) {
     return 0;
 }
 
-// Host-buffer scoring: chunks of prompts are staged through two pinned slots so that the copy of
-// chunk c+1 overlaps the kernel of chunk c and the read-back of chunk c-1.
+// Host-buffer scoring.  Chunks of prompts flow through two slots and three streams so that the H2D copy
+// of chunk c+1, the kernel of chunk c and the D2H of chunk c-1 overlap (two DMA engines + SMs):
+//   copy_stream : staging -> d_tok/d_off/...      (records ev_h2d[slot])
+//   x->stream   : score kernel                      (waits ev_h2d, records ev_k[slot])
+//   d2h_stream  : results -> pinned host            (waits ev_k, records ev_done[slot])
+// Caller buffers that are already pinned are used directly (no staging memcpy).
 int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
                const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys) {
     if (n < 0 || !tok_off) return fail(KVIDX_EINVAL, "bad arguments");
     if (n == 0) return 0;
     int rc = check_csr(tok_off, n);
     if (rc) return rc;
+    if (tok_off[n] > tok_off[0] && !tok) return fail(KVIDX_EINVAL, "NULL tokens");
     std::lock_guard<std::mutex> g(x->mu);
     CK(cudaSetDevice(x->device));
     const uint32_t P = x->tv.max_pods, FW = x->tv.filter_words;
     const bool sparse = sp_cnt != nullptr;
-    const size_t out_row = sparse ? (size_t)kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 1 : (size_t)P * sizeof(double);
-    // chunking: bound staged tokens to ~64 MiB and output to ~64 MiB per slot
-    const int64_t kMaxTokChunk = 16ll << 20;      // tokens
-    const int64_t kMaxRowsChunk = std::max<int64_t>(1, (64ll << 20) / (int64_t)out_row);
-    const bool tok_pinned = is_device_accessible_host(tok);
-    int64_t i0 = 0;
-    int slot = 0;
+    const size_t out_row = sparse ? (size_t)kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 2 : (size_t)P * sizeof(double) + 1;
+    const int64_t kMaxTokChunk = 8ll << 20;       // tokens per chunk (32 MiB): small enough to pipeline, large enough for DMA
+    const int64_t kMaxRowsChunk = std::max<int64_t>(1, (32ll << 20) / (int64_t)out_row);
+    const bool tok_pinned = tok && is_device_accessible_host(tok);
+    const bool out_pinned = !sparse && dense && is_device_accessible_host(dense) && (!has_keys || is_device_accessible_host(has_keys));
+    cudaStream_t s_k = x->stream, s_in = x->copy_stream, s_out = x->d2h_stream;
     struct Pending { bool live = false; int64_t i0 = 0, cnt = 0; } pend[2];
     auto drain = [&](int s) -> int {
         if (!pend[s].live) return 0;
         CK(cudaEventSynchronize(x->ev_done[s]));
+        pend[s].live = false;
+        if (out_pinned) return 0;                 // results were written straight into the caller's buffers
         const int64_t c = pend[s].cnt, b = pend[s].i0;
         const uint8_t* ho = x->h_out[s].as<uint8_t>();
         if (!sparse) {
@@ -205,69 +211,79 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
             memcpy(sp_cnt + b, ho + o, (size_t)c); o += (size_t)c;
             if (has_keys) memcpy(has_keys + b, ho + o, (size_t)c);
         }
-        pend[s].live = false;
         return 0;
     };
+    // the first chunk must see everything already queued on the handle's stream (earlier writes)
+    CK(cudaEventRecord(x->ev_k[0], s_k));
+    CK(cudaStreamWaitEvent(s_in, x->ev_k[0], 0));
+    int64_t i0 = 0;
+    int slot = 0;
     while (i0 < n) {
         int64_t i1 = i0;
         while (i1 < n && (i1 - i0) < kMaxRowsChunk && (tok_off[i1 + 1] - tok_off[i0]) <= kMaxTokChunk) ++i1;
-        if (i1 == i0) i1 = i0 + 1;    // a single prompt larger than the chunk budget
+        if (i1 == i0) i1 = i0 + 1;                // a single prompt larger than the chunk budget
         const int64_t c = i1 - i0, tb = tok_off[i0], nt = tok_off[i1] - tb;
-        rc = drain(slot);
+        rc = drain(slot);                         // slot's previous results are home; its device buffers are free
         if (rc) return rc;
-        // stage
         CK(x->d_tok[slot].need((size_t)std::max<int64_t>(nt, 1) * 4 + 64));
         CK(x->d_off[slot].need((size_t)(c + 1) * 8));
-        const uint32_t* src = tok + tb;
-        size_t stage_bytes = (size_t)(c + 1) * 8 + (model ? (size_t)c * 4 : 0) + (filter ? (size_t)c * FW * 8 : 0) + (tok_pinned ? 0 : (size_t)nt * 4);
+        const size_t stage_bytes = (size_t)(c + 1) * 8 + (model ? (size_t)c * 4 : 0) + (filter ? (size_t)c * FW * 8 : 0) +
+                                   (tok_pinned ? 0 : (size_t)nt * 4);
         CK(x->h_stage[slot].need(stage_bytes + 64));
         uint8_t* hs = x->h_stage[slot].as<uint8_t>();
         size_t o = 0;
         memcpy(hs + o, tok_off + i0, (size_t)(c + 1) * 8);
-        CK(cudaMemcpyAsync(x->d_off[slot].p, hs + o, (size_t)(c + 1) * 8, cudaMemcpyHostToDevice, x->stream)); o += (size_t)(c + 1) * 8;
+        CK(cudaMemcpyAsync(x->d_off[slot].p, hs + o, (size_t)(c + 1) * 8, cudaMemcpyHostToDevice, s_in)); o += (size_t)(c + 1) * 8;
         const uint32_t* dm = nullptr; const uint64_t* df = nullptr;
         if (model) {
             CK(x->d_model[slot].need((size_t)c * 4));
             memcpy(hs + o, model + i0, (size_t)c * 4);
-            CK(cudaMemcpyAsync(x->d_model[slot].p, hs + o, (size_t)c * 4, cudaMemcpyHostToDevice, x->stream)); o += (size_t)c * 4;
+            CK(cudaMemcpyAsync(x->d_model[slot].p, hs + o, (size_t)c * 4, cudaMemcpyHostToDevice, s_in)); o += (size_t)c * 4;
             dm = x->d_model[slot].as<uint32_t>();
         }
         if (filter) {
             CK(x->d_filter[slot].need((size_t)c * FW * 8));
             memcpy(hs + o, filter + i0 * FW, (size_t)c * FW * 8);
-            CK(cudaMemcpyAsync(x->d_filter[slot].p, hs + o, (size_t)c * FW * 8, cudaMemcpyHostToDevice, x->stream)); o += (size_t)c * FW * 8;
+            CK(cudaMemcpyAsync(x->d_filter[slot].p, hs + o, (size_t)c * FW * 8, cudaMemcpyHostToDevice, s_in)); o += (size_t)c * FW * 8;
             df = x->d_filter[slot].as<uint64_t>();
         }
         if (nt > 0) {
-            if (tok_pinned) {
-                CK(cudaMemcpyAsync(x->d_tok[slot].p, src, (size_t)nt * 4, cudaMemcpyHostToDevice, x->stream));
-            } else {
-                memcpy(hs + o, src, (size_t)nt * 4);
-                CK(cudaMemcpyAsync(x->d_tok[slot].p, hs + o, (size_t)nt * 4, cudaMemcpyHostToDevice, x->stream));
-            }
+            const uint32_t* src = tok + tb;
+            if (!tok_pinned) { memcpy(hs + o, src, (size_t)nt * 4); src = reinterpret_cast<const uint32_t*>(hs + o); }
+            CK(cudaMemcpyAsync(x->d_tok[slot].p, src, (size_t)nt * 4, cudaMemcpyHostToDevice, s_in));
         }
-        // outputs
-        CK(x->d_out[slot].need((size_t)c * out_row + (size_t)c + 64));
-        CK(x->h_out[slot].need((size_t)c * out_row + (size_t)c + 64));
+        CK(cudaEventRecord(x->ev_h2d[slot], s_in));
+        // kernel
+        CK(x->d_out[slot].need((size_t)c * out_row + 64));
+        if (!out_pinned) CK(x->h_out[slot].need((size_t)c * out_row + 64));
         uint8_t* dout = x->d_out[slot].as<uint8_t>();
         ScoreOut so{};
-        size_t total;
         if (!sparse) {
             so.dense = reinterpret_cast<double*>(dout);
             so.has_keys = dout + (size_t)c * P * sizeof(double);
-            total = (size_t)c * P * sizeof(double) + (size_t)c;
         } else {
             size_t q = 0;
             so.sp_scores = reinterpret_cast<double*>(dout + q); q += (size_t)c * kMaxEnt * sizeof(double);
             so.sp_pods = reinterpret_cast<uint16_t*>(dout + q); q += (size_t)c * kMaxEnt * sizeof(uint16_t);
             so.sp_cnt = dout + q; q += (size_t)c;
             so.has_keys = dout + q; q += (size_t)c;
-            total = q;
         }
-        rc = launch_score(x, x->d_tok[slot].as<uint32_t>(), x->d_off[slot].as<int64_t>(), tb, c, dm, model0, df, so, x->stream);
+        CK(cudaStreamWaitEvent(s_k, x->ev_h2d[slot], 0));
+        rc = launch_score(x, x->d_tok[slot].as<uint32_t>(), x->d_off[slot].as<int64_t>(), tb, c, dm, model0, df, so, s_k);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(x->h_out[slot].p, dout, total, cudaMemcpyDeviceToHost, x->stream));
-        CK(cudaEventRecord(x->ev_done[slot], x->stream));
+        CK(cudaEventRecord(x->ev_k[slot], s_k));
+        // (slot reuse is safe without further stream waits: drain(slot) host-waits on ev_done[slot], which is
+        //  recorded after this kernel and its read-back)
+        // read back
+        CK(cudaStreamWaitEvent(s_out, x->ev_k[slot], 0));
+        if (out_pinned) {
+            CK(cudaMemcpyAsync(dense + i0 * (int64_t)P, so.dense, (size_t)c * P * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (has_keys) CK(cudaMemcpyAsync(has_keys + i0, so.has_keys, (size_t)c, cudaMemcpyDeviceToHost, s_out));
+        } else {
+            const size_t total = sparse ? (size_t)c * (kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 2) : (size_t)c * (P * sizeof(double) + 1);
+            CK(cudaMemcpyAsync(x->h_out[slot].p, dout, total, cudaMemcpyDeviceToHost, s_out));
+        }
+        CK(cudaEventRecord(x->ev_done[slot], s_out));
         pend[slot].live = true; pend[slot].i0 = i0; pend[slot].cnt = c;
         slot ^= 1;
         i0 = i1;
@@ -356,10 +372,12 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (prop.major < 10) { delete x; return fail(KVIDX_ECUDA, "device sm_%d%d is not Blackwell; libkvidx is built for sm_100a only", prop.major, prop.minor); }
     CK(cudaStreamCreateWithFlags(&x->own_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking));
     x->stream = x->own_stream;
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&x->ev_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&x->ev_k[i], cudaEventDisableTiming));
     }
     uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(2 * c.capacity, 1024));
     if (slots < 1024) slots = 1024;
@@ -393,6 +411,7 @@ void kvidx_destroy(kvidx_t* x) {
         x->d_out[i].release(); x->d_aux[i].release(); x->h_stage[i].release(); x->h_out[i].release();
         if (x->ev_h2d[i]) cudaEventDestroy(x->ev_h2d[i]);
         if (x->ev_done[i]) cudaEventDestroy(x->ev_done[i]);
+        if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]);
     }
     x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
     if (x->tv.req) cudaFree(x->tv.req);
@@ -402,6 +421,7 @@ void kvidx_destroy(kvidx_t* x) {
     if (x->h_cnt) cudaFreeHost(x->h_cnt);
     if (x->own_stream) cudaStreamDestroy(x->own_stream);
     if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
+    if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
     delete x;
 }
 

@@ -165,9 +165,10 @@ struct Oracle {
                 if (!pc || pc->cache.len() == 0) return 0;            // :119-122 cut
                 if (!filter || filter->empty()) {
                     auto& v = out[k];
+                    v.clear();                                        // :128 assigns (a repeated key overwrites)
                     pc->cache.keys_oldest_first([&](uint16_t e) { v.push_back(e); });
                 } else {
-                    pc->cache.keys_oldest_first([&](uint16_t e) {
+                    pc->cache.keys_oldest_first([&](uint16_t e) {       // :130-135 appends (a repeated key accumulates)
                         if (filter->count(KVIDX_PT_POD(e))) out[k].push_back(e);
                     });
                 }

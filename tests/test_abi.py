@@ -1,0 +1,55 @@
+"""CPU: libkvidx.so loads, exports every symbol include/kvidx.h declares, and refuses to run
+without a GPU (no CPU fallback).  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import conftest
+import kvidx
+from kvidx import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "kvidx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kvidx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    names = _declared_symbols()
+    assert len(names) >= 24
+    L = C.CDLL(_native.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libkvidx.so does not export %s" % n
+        assert n in _native.SYMBOLS, "ctypes binding misses %s" % n
+    assert sorted(_native.SYMBOLS) == names
+
+
+def test_abi_version_and_struct_layout():
+    L = kvidx.load()
+    assert L.kvidx_abi_version() == 1
+    cfg = _native.Config()
+    L.kvidx_config_default(C.byref(cfg))
+    assert cfg.struct_size == C.sizeof(_native.Config) == 208
+    assert (cfg.block_size, cfg.pods_per_key, cfg.max_pods, cfg.n_tier_weights) == (16, 10, 256, 2)
+    assert cfg.init_hash == 0xCBF29CE484222325 and (cfg.tier_weight[0], cfg.tier_weight[1]) == (1.0, 0.8)
+    assert _native.EVENT_DTYPE.itemsize == 40 and C.sizeof(_native.Stats) == 64
+
+
+def test_host_helpers():
+    assert kvidx.fnv64a(b"") == 0xCBF29CE484222325 and kvidx.fnv64a(b"42") == 571532774284038691
+    L = kvidx.load()
+    assert L.kvidx_fnv32a(b"a", 1) == 0xE40C292C
+    assert L.kvidx_queue_index(b"pod-1", 5, 4) == L.kvidx_fnv32a(b"pod-1", 5) % 4
+    assert kvidx.podtier(5, 1) == 0x51
+
+
+@pytest.mark.skipif(conftest.HAS_CUDA, reason="checks the no-GPU failure mode")
+def test_create_fails_loudly_without_gpu():
+    with pytest.raises(kvidx.KvidxError) as ei:
+        kvidx.Index()
+    assert ei.value.code == kvidx.ECUDA and "no CPU fallback" in str(ei.value)
