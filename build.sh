@@ -2,7 +2,7 @@
 # Builds libkvidx.so (sm_100a only) in-tree.  Usage: ./build.sh [extra nvcc flags]
 set -e
 cd "$(dirname "$0")"
-OUT=llm-d-kv-cache-manager_b200/lib
+OUT=${KVIDX_OUT:-llm-d-kv-cache-manager_b200/lib}
 mkdir -p $OUT
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall -shared \
      -Xptxas -v "$@" -o $OUT/libkvidx.so llm-d-kv-cache-manager_b200/csrc/kvidx.cu 2>&1

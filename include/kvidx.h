@@ -73,7 +73,8 @@ typedef struct kvidx_config {
     uint32_t pods_per_key;     /* PodCacheSize; 0 -> 10; must be 1..10                          */
     uint64_t init_hash;        /* FNV-64a(HashSeed) (token_processor.go:81-90); use kvidx_fnv64a */
     uint64_t capacity;         /* InMemoryIndexConfig.Size: max resident keys; 0 -> 1<<20       */
-    uint64_t table_slots;      /* open-addressing slots (power of two); 0 -> 2*capacity rounded */
+    uint64_t table_slots;      /* open-addressing slots (power of two); 0 -> 4*capacity rounded up
+                                  (load factor <= 0.25: a probe almost always ends in its home pair) */
     uint32_t max_pods;         /* dense score-row width P (1..4096); 0 -> 256                   */
     uint32_t n_tier_weights;   /* entries of tier_weight[] that are configured                  */
     double   tier_weight[KVIDX_MAX_TIERS]; /* weight of tier id i; ids >= n_tier_weights score 1.0

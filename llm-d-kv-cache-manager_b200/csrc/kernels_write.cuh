@@ -37,6 +37,7 @@ __device__ __forceinline__ uint32_t slot_remove_entry(ReqSlot* s, uint32_t count
     for (uint32_t j = 0; j < count; ++j) {
         if (e[j] == pt) {
             for (uint32_t q = j; q + 1 < count; ++q) e[q] = e[q + 1];
+            e[count - 1] = 0;      // vacated position is zeroed: slots with equal live entries are bitwise equal
             return count - 1;
         }
     }
@@ -166,7 +167,7 @@ __global__ void rebuild_req_kernel(const ReqSlot* __restrict__ old_tab, uint64_t
     const uint4 a = src[0], b = src[1];
     if (meta_state(b.w) != kStateFull) return;
     const uint64_t tag = ((uint64_t)a.y << 32) | a.x;
-    uint64_t j = home_of(tag, meta_model(b.w)) & new_mask;
+    uint64_t j = slot_home(tag, meta_model(b.w), new_mask);
     for (;;) {
         if (atomicCAS(&new_tab[j].meta, 0u, b.w | kLockBit) == 0u) {
             uint4* dst = reinterpret_cast<uint4*>(new_tab + j);
@@ -185,7 +186,7 @@ __global__ void rebuild_eng_kernel(const EngSlot* __restrict__ old_tab, uint64_t
     if (i >= old_slots) return;
     const EngSlot s = old_tab[i];
     if (meta_state(s.meta) != kStateFull) return;
-    uint64_t j = home_of(s.ehash, meta_model(s.meta)) & new_mask;
+    uint64_t j = slot_home(s.ehash, meta_model(s.meta), new_mask);
     for (;;) {
         if (atomicCAS(&new_tab[j].meta, 0u, s.meta | kLockBit) == 0u) {
             new_tab[j].ehash = s.ehash; new_tab[j].rhash = s.rhash; new_tab[j].stamp = s.stamp;

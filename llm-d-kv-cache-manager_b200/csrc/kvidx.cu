@@ -14,6 +14,7 @@
 #include "kernels_v1.cuh"
 #include "kernels_write.cuh"
 #include "kernels_score.cuh"
+#include "kernels_rounds.cuh"
 
 using namespace kvx;
 
@@ -91,6 +92,9 @@ struct kvidx {
     DevBuf d_tok[2], d_off[2], d_model[2], d_filter[2], d_out[2], d_aux[2], d_misc, d_ev, d_hash, d_evtok, d_qoff;
     PinBuf h_stage[2], h_out[2], h_misc;
     int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
+    int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
+    int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
+    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst;
 };
 
 namespace {
@@ -147,15 +151,54 @@ int ensure_room(kvidx* x, uint64_t incoming) {
 
 struct ScoreOut { double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* sp_cnt; uint8_t* has_keys; };
 
-// Launch the score kernel over device-resident inputs.
+// Large batches: alternating hash / probe rounds (kernels_rounds.cuh).  max_blocks < 0: computed on the device.
+int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
+                        const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
+                        int64_t max_blocks) {
+    CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(64));
+    CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState)));
+    RoundBufs rb{};
+    rb.act[0] = x->r_act0.as<uint32_t>(); rb.act[1] = x->r_act1.as<uint32_t>();
+    rb.n_act = x->r_cnt.as<unsigned int>();
+    unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(x->r_cnt.as<unsigned char>() + 16);
+    rb.hstate = x->r_hstate.as<uint64_t>(); rb.keys = x->r_keys.as<uint64_t>(); rb.pst = x->r_pst.as<PromptState>();
+    ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
+    CK(cudaMemsetAsync(x->r_cnt.p, 0, 64, st));
+    rounds_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, rb, x->tv.block_size, d_maxb);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    if (max_blocks < 0) {
+        unsigned long long mb = 0;
+        CK(cudaMemcpyAsync(&mb, d_maxb, sizeof mb, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        max_blocks = (int64_t)mb;
+    }
+    int64_t rounds = (max_blocks + kRoundBlocks - 1) / kRoundBlocks;
+    if (rounds < 1) rounds = 1;                       // round 0 also retires the prompts that have no full block
+    const unsigned hgrid = (unsigned)std::min<int64_t>((n + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * 4);
+    const unsigned pgrid = (unsigned)std::min<int64_t>((n * 32 + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * 8);
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int cur = (int)(r & 1);
+        hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), st>>>(x->tv, a, rb, cur, (int)r);
+        probe_round_kernel<<<pgrid, kProbeThreads, 0, st>>>(x->tv, a, rb, cur, (int)r);
+        x->launches += 2;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// Launch the score kernel(s) over device-resident inputs.
 int launch_score(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
-                 const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st) {
+                 const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
+                 int64_t max_blocks = -1) {
     if (n <= 0) return 0;
     if (x->score_kernel == 1) {
         const int T = 128;
         score_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
                                                                   o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys);
         x->launches += 1;
+    } else if (x->tv.block_size == 16 && n < (1ll << 32) && (x->score_path == 2 || (x->score_path == 0 && n >= x->rounds_min))) {
+        return launch_score_rounds(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks);
     } else {
         int rc = launch_score_tuned(x->tv, x->sm_count, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
                                     o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, &x->d_cnt->pad, st, &x->launches);
@@ -269,7 +312,9 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
             so.has_keys = dout + q; q += (size_t)c;
         }
         CK(cudaStreamWaitEvent(s_k, x->ev_h2d[slot], 0));
-        rc = launch_score(x, x->d_tok[slot].as<uint32_t>(), x->d_off[slot].as<int64_t>(), tb, c, dm, model0, df, so, s_k);
+        int64_t maxb = 0;
+        for (int64_t q = i0; q < i1; ++q) maxb = std::max<int64_t>(maxb, (tok_off[q + 1] - tok_off[q]) / x->tv.block_size);
+        rc = launch_score(x, x->d_tok[slot].as<uint32_t>(), x->d_off[slot].as<int64_t>(), tb, c, dm, model0, df, so, s_k, maxb);
         if (rc) return rc;
         CK(cudaEventRecord(x->ev_k[slot], s_k));
         // (slot reuse is safe without further stream waits: drain(slot) host-waits on ev_done[slot], which is
@@ -379,7 +424,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
         CK(cudaEventCreateWithFlags(&x->ev_done[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&x->ev_k[i], cudaEventDisableTiming));
     }
-    uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(2 * c.capacity, 1024));
+    uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(4 * c.capacity, 1024));
     if (slots < 1024) slots = 1024;
     TableView& t = x->tv;
     t.req_mask = slots - 1; t.eng_mask = slots - 1;
@@ -396,6 +441,9 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     t.cnt = x->d_cnt;
     CK(cudaStreamSynchronize(x->stream));
     if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
+    if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
+    if (rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = score_tuned_init();
     if (rc) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     *out = x;
@@ -413,6 +461,7 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_done[i]) cudaEventDestroy(x->ev_done[i]);
         if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]);
     }
+    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release();
     x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
     if (x->tv.req) cudaFree(x->tv.req);
     if (x->tv.eng) cudaFree(x->tv.eng);

@@ -38,6 +38,11 @@ struct __align__(32) EngSlot {
 };
 static_assert(sizeof(EngSlot) == 32, "engine slot is 32 bytes");
 
+// Home slot: even-aligned so that probe positions 0 and 1 share one 64-byte segment and the read path can
+// fetch both with a single coalesced 64-byte access (then linear probing continues at home+2).
+__host__ __device__ __forceinline__ uint64_t slot_home(uint64_t hash, uint32_t model, uint64_t mask) {
+    return home_of(hash, model) & mask & ~1ull;
+}
 __host__ __device__ __forceinline__ uint32_t meta_state(uint32_t m) { return m & kStateMask; }
 __host__ __device__ __forceinline__ uint32_t meta_count(uint32_t m) { return (m >> 4) & 0xfu; }
 __host__ __device__ __forceinline__ uint32_t meta_model(uint32_t m) { return m >> 16; }
@@ -92,7 +97,7 @@ __device__ __forceinline__ uint32_t slot_ent(const SlotWords& w, int j) {
 
 // Finds the FULL slot holding (model, tag).  Returns false at the first EMPTY slot.
 __device__ __forceinline__ bool req_find(const TableView& t, uint32_t model, uint64_t tag, SlotWords& w, uint64_t* slot_out = nullptr) {
-    uint64_t i = home_of(tag, model) & t.req_mask;
+    uint64_t i = slot_home(tag, model, t.req_mask);
     const uint32_t tlo = (uint32_t)tag, thi = (uint32_t)(tag >> 32);
     for (;;) {
         w = load_slot(t.req + i);
@@ -107,7 +112,7 @@ __device__ __forceinline__ bool req_find(const TableView& t, uint32_t model, uin
 }
 
 __device__ __forceinline__ bool eng_find(const TableView& t, uint32_t model, uint64_t ehash, uint64_t* rhash, uint64_t* slot_out = nullptr) {
-    uint64_t i = home_of(ehash, model) & t.eng_mask;
+    uint64_t i = slot_home(ehash, model, t.eng_mask);
     for (;;) {
         const EngSlot* s = t.eng + i;
         const uint32_t m = ld_volatile_u32(&s->meta);
@@ -131,7 +136,7 @@ __device__ __forceinline__ bool eng_find(const TableView& t, uint32_t model, uin
 // Returns the slot index of (model, tag) with the lock held; *created tells whether the slot
 // was claimed fresh (count 0, tag written).  If must_exist and the key is absent returns ~0.
 __device__ __forceinline__ uint64_t req_lock(const TableView& t, uint32_t model, uint64_t tag, bool must_exist, bool* created) {
-    uint64_t i = home_of(tag, model) & t.req_mask;
+    uint64_t i = slot_home(tag, model, t.req_mask);
     *created = false;
     for (;;) {
         ReqSlot* s = t.req + i;
@@ -165,7 +170,7 @@ __device__ __forceinline__ void req_unlock(ReqSlot* s, uint32_t new_meta) {
 }
 
 __device__ __forceinline__ uint64_t eng_lock(const TableView& t, uint32_t model, uint64_t ehash, bool must_exist, bool* created) {
-    uint64_t i = home_of(ehash, model) & t.eng_mask;
+    uint64_t i = slot_home(ehash, model, t.eng_mask);
     *created = false;
     for (;;) {
         EngSlot* s = t.eng + i;

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "lib", "libkvidx.so")
+LIB_PATH = os.environ.get("KVIDX_LIB") or os.path.join(_PKG, "lib", "libkvidx.so")   # KVIDX_LIB: experiment builds only
 
 E = 10            # KVIDX_MAX_PODS_PER_KEY
 MAX_TIERS = 16

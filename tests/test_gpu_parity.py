@@ -191,9 +191,10 @@ def _random_stream(rng, n_steps, BS, P, NT, docs, model=0):
     return np.array(ev, EVENT_DTYPE), np.array(hs, np.uint64), np.array(tk, np.uint64).astype(np.uint32)
 
 
-@pytest.mark.parametrize("seed,BS", [(11, 16), (12, 16), (13, 4)])
-def test_random_event_stream_and_queries_vs_cpp_oracle(seed, BS):
+@pytest.mark.parametrize("seed,BS,path", [(11, 16, "fused"), (12, 16, "rounds"), (13, 4, "fused"), (14, 16, "rounds")])
+def test_random_event_stream_and_queries_vs_cpp_oracle(seed, BS, path, monkeypatch):
     """Differential test on a few thousand events (sequential replay => identical linearisation)."""
+    _select_path(monkeypatch, path)
     rng = np.random.default_rng(seed)
     P, NT = 40, 3
     w = (1.0, 0.8, 0.3)
@@ -264,11 +265,22 @@ def test_batched_events_per_pod_order_vs_oracle():
     assert np.array_equal(s1, s2)
 
 
-@pytest.mark.parametrize("kernel", ["v1", "tuned"])
+def _select_path(monkeypatch, path):
+    """v1: thread-per-prompt kernel; fused: persistent lane-worker kernel; rounds: hash/probe round pipeline."""
+    if path == "v1":
+        monkeypatch.setenv("KVIDX_SCORE_KERNEL", "v1")
+    else:
+        monkeypatch.setenv("KVIDX_SCORE_PATH", path)
+
+
+PATHS = ["v1", "fused", "rounds"]
+
+
+@pytest.mark.parametrize("kernel", PATHS)
 def test_synth_config2_shape_vs_oracle_and_closed_form(kernel, monkeypatch):
     """BASELINE config #2 shape at reduced size (2K-token prompts, 64 pods): fill through the write path,
     then scores bit-exact vs the C++ oracle and vs the generator's closed form."""
-    monkeypatch.setenv("KVIDX_SCORE_KERNEL", kernel)
+    _select_path(monkeypatch, kernel)
     wl = synth.Workload(2, 2048, 1 << 15, 64)
     ix, co = _index_pair(capacity=1 << 16, max_pods=64)
     ev, hs, tk = wl.fill_events(0, wl.D)
@@ -285,9 +297,11 @@ def test_synth_config2_shape_vs_oracle_and_closed_form(kernel, monkeypatch):
     assert np.array_equal(s1, wl.expected_scores(doc, m))
 
 
-def test_tuned_kernel_ragged_misaligned_and_many_prompts(monkeypatch):
-    """The persistent kernel's lane refill, unaligned prompt starts (TMA fallback path), empty and
-    sub-block prompts, against the v1 kernel and the oracle."""
+@pytest.mark.parametrize("kernel", ["fused", "rounds"])
+def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
+    """Lane refill / round lists, unaligned prompt starts (per-lane staging fallback), empty and sub-block
+    prompts, pod filters, against the oracle."""
+    _select_path(monkeypatch, kernel)
     rng = np.random.default_rng(31)
     wl = synth.Workload(9, 512, 1 << 13, 32)
     ix, co = _index_pair(capacity=1 << 14, max_pods=32)
@@ -305,6 +319,16 @@ def test_tuned_kernel_ragged_misaligned_and_many_prompts(monkeypatch):
     s_o, h_o, _, _ = co.score_batch(tok, off, n_threads=4)
     assert np.array_equal(h_t, h_o) and np.array_equal(s_t, s_o), np.argwhere(s_t != s_o)[:5]
     assert (np.diff(off) % 4 != 0).any()        # some prompt starts are not 16-byte aligned
+    fm = np.zeros((len(prompts), ix.filter_words), np.uint64)
+    for i in range(0, len(prompts), 2):
+        fm[i] = filter_mask(rng.choice(32, size=int(rng.integers(1, 6)), replace=False).tolist(), ix.filter_words)
+    s_t, _ = ix.score_batch(tok, off, filter_mask=fm)
+    s_o, _, _, _ = co.score_batch(tok, off, filter_mask=fm, n_threads=4)
+    assert np.array_equal(s_t, s_o), np.argwhere(s_t != s_o)[:5]
+    sp_p, sp_s, sp_c, _ = ix.score_batch_sparse(tok, off, filter_mask=fm)
+    for i in range(0, len(prompts), 97):
+        got = {int(sp_p[i, j]): float(sp_s[i, j]) for j in range(sp_c[i])}
+        assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
 
 
 def test_rebuild_after_tombstones():
