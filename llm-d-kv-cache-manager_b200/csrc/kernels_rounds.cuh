@@ -32,21 +32,28 @@ constexpr int kProbeThreads = 256;
 struct __align__(8) PromptState {        // walk state carried between rounds (only for prompts that continue)
     double sc[kMaxEnt];
     uint16_t pod[kMaxEnt];
+    uint32_t pat[6];                     // entry words + count of the last scored block's slot
     uint16_t alive;                      // bitmask over [0,k)
     uint8_t k;
     uint8_t pad;
+    uint8_t bt[kMaxEnt];                 // tier giving pod q its max weight in that slot (0xff: 0.0)
+    uint8_t pad2[2];
 };
 
 struct RoundBufs {
     uint32_t* act[2];                    // active prompt lists (ping-pong)
     unsigned int* n_act;                 // [2] list lengths
     uint64_t* hstate;                    // chain hash after the last hashed block, per prompt
-    uint64_t* keys;                      // [n_act][kRoundBlocks] keys of the current round
+    uint64_t* keys;                      // [kRoundBlocks][n_prompts] keys of the current round, block-major: key of
+                                         // block j of list slot i at keys[j * n_prompts + i] (coalesced both ways)
+    uint32_t* nbr;                       // [n_act] per list slot: blocks hashed this round | (more blocks follow) << 8
     PromptState* pst;                    // per prompt
 };
 
+constexpr int kHashChunk = 1;            // blocks staged per copy step (2 = 128-byte accesses was measured: fewer, longer DRAM
+                                         // accesses but only 24 resident warps/SM -> 6 % slower; the kernel is pipe bound)
 template <int BS> struct HashSmem {
-    static constexpr int kRow = BS * 4 + 16;
+    static constexpr int kRow = kHashChunk * BS * 4 + 16;   // 144 B: the four LDS.128 of a block stay conflict free
     unsigned char tok[kHashThreads / 32][2][32 * kRow];
 };
 
@@ -75,46 +82,58 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
             const int64_t nblk = (e - b) / BS;
             const int64_t first = (int64_t)round * kRoundBlocks;
             nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
+            rb.nbr[i] = (uint32_t)nb | ((first + nb < nblk) ? 0x100u : 0u);
             src = a.tok + b + first * BS;
             aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
             h = round == 0 ? t.init_hash : rb.hstate[p];
         }
         const int nb_max = __reduce_max_sync(0xffffffffu, nb);
-        uint64_t* krow = rb.keys + (size_t)i * kRoundBlocks;
-        auto stage = [&](int s, int b) {
-            const bool issue = b < nb;
-            const unsigned long long srcv = (issue && aligned) ? (unsigned long long)(uintptr_t)(src + (size_t)b * BS) : 0ull;
+        // stage chunk c (kHashChunk blocks) of every lane's prompt: 4*kHashChunk lanes move one prompt's contiguous bytes.
+        auto stage = [&](int s, int c) {
+            const int b0 = c * kHashChunk;
+            const bool issue = b0 < nb;
+            const int nbytes = issue ? min(kHashChunk, nb - b0) * BS * 4 : 0;
+            const unsigned long long srcv = (issue && aligned) ? (unsigned long long)(uintptr_t)(src + (size_t)b0 * BS) : 0ull;
             __syncwarp();
+            constexpr int LPP = 4 * kHashChunk;             // lanes that move one prompt's chunk (16 B each)
+            constexpr int PPI = 32 / LPP;                   // prompts per copy instruction
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int q = 8 * r + (lane >> 2);
+            for (int r = 0; r < 32 / PPI; ++r) {
+                const int q = PPI * r + lane / LPP;
                 const unsigned long long sp = __shfl_sync(0xffffffffu, srcv, q);
-                if (sp) cp_async_16(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane & 3) * 16]), reinterpret_cast<const char*>(sp) + (lane & 3) * 16);
+                const int nby = kHashChunk == 1 ? BS * 4 : __shfl_sync(0xffffffffu, nbytes, q);
+                if (sp && (lane % LPP) * 16 < nby)
+                    cp_async_16(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane % LPP) * 16]), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16);
             }
             cp_async_commit();
             if (issue && !aligned) {
                 uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tok[wid][s][lane * SM::kRow]);
-                const uint32_t* g = src + (size_t)b * BS;
-                for (int j = 0; j < BS; ++j) dst[j] = __ldg(g + j);
+                const uint32_t* g = src + (size_t)b0 * BS;
+                for (int j = 0; j < nbytes / 4; ++j) dst[j] = __ldg(g + j);
             }
         };
         stage(0, 0);
-        for (int b = 0; b < nb_max; ++b) {
-            stage((b + 1) & 1, b + 1);
+        const int nchunks = (nb_max + kHashChunk - 1) / kHashChunk;
+        for (int c = 0; c < nchunks; ++c) {
+            stage((c + 1) & 1, c + 1);
             cp_async_wait<1>();
             __syncwarp();
-            Fnv f;
-            f.begin_block(h, BS);
-            const uint4* tp = reinterpret_cast<const uint4*>(&sm.tok[wid][b & 1][lane * SM::kRow]);
-            const uint4 v0 = tp[0], v1 = tp[1];
-            f.token(v0.x); f.token(v0.y); f.token(v0.z); f.token(v0.w);
-            const uint4 v2 = tp[2];
-            f.token(v1.x); f.token(v1.y); f.token(v1.z); f.token(v1.w);
-            const uint4 v3 = tp[3];
-            f.token(v2.x); f.token(v2.y); f.token(v2.z); f.token(v2.w);
-            f.token(v3.x); f.token(v3.y); f.token(v3.z); f.token(v3.w);
-            const uint64_t key = f.end_block();
-            if (b < nb) { h = key; krow[b] = key; }
+#pragma unroll
+            for (int u = 0; u < kHashChunk; ++u) {
+                const int b = c * kHashChunk + u;
+                Fnv f;
+                f.begin_block(h, BS);
+                const uint4* tp = reinterpret_cast<const uint4*>(&sm.tok[wid][c & 1][lane * SM::kRow + u * BS * 4]);
+                const uint4 v0 = tp[0], v1 = tp[1];
+                f.token(v0.x); f.token(v0.y); f.token(v0.z); f.token(v0.w);
+                const uint4 v2 = tp[2];
+                f.token(v1.x); f.token(v1.y); f.token(v1.z); f.token(v1.w);
+                const uint4 v3 = tp[3];
+                f.token(v2.x); f.token(v2.y); f.token(v2.z); f.token(v2.w);
+                f.token(v3.x); f.token(v3.y); f.token(v3.z); f.token(v3.w);
+                const uint64_t key = f.end_block();
+                if (b < nb) { h = key; rb.keys[(size_t)b * a.n_prompts + i] = key; }
+            }
         }
         cp_async_wait<0>();
         __syncwarp();
@@ -136,117 +155,160 @@ __device__ __forceinline__ uint32_t ent_of(uint32_t e0, uint32_t e1, uint32_t e2
     return (j & 1) ? (word >> 16) : (word & 0xffffu);
 }
 
-__global__ void __launch_bounds__(kProbeThreads)
-probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
-    __shared__ double s_weight[16];
-    if (threadIdx.x < 16) s_weight[threadIdx.x] = t.weight[threadIdx.x];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned int n_act = rb.n_act[cur];
-    const unsigned int total_warps = gridDim.x * (kProbeThreads / 32);
-    for (unsigned int i = blockIdx.x * (kProbeThreads / 32) + wid; i < n_act; i += total_warps) {
-        const uint32_t p = rb.act[cur][i];
-        const int64_t tb = a.tok_off[p] - a.tok_base, te = a.tok_off[p + 1] - a.tok_base;
-        const int64_t nblk = (te - tb) / t.block_size;
-        const int64_t first = (int64_t)round * kRoundBlocks;
-        const int nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
-        const uint32_t mdl = a.model ? a.model[p] : a.model0;
+// Kernel P, lane-per-prompt.  (Two warp-per-prompt versions came first -- 32 lanes probing a prompt's 32 keys at
+// once, then the same software-pipelined.  Both cost ~700 issue slots per prompt-round because the walk itself
+// runs on <= 10 lanes while the other 22 idle, and stayed at ~25 % issue utilisation: profiles/r1d_*.)  Here a
+// warp walks 32 prompts in lockstep, one block per iteration: every instruction serves 32 prompts, the 32 lanes'
+// probes are 32 independent 64-byte reads, and the slot pair for block j+1 is in flight while block j is scored.
+struct WalkSmem {
+    struct Warp {
+        double sc[kMaxEnt][32];
+        uint16_t pod[kMaxEnt][32];
+        uint8_t bt[kMaxEnt][32];
+    };
+    Warp w[kProbeThreads / 32];
+    double weight[16];
+};
 
-        // ---- 1. all keys of the round probed at once: lane j <-> block first+j ----
-        bool hit = false;
-        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0, cnt = 0;
-        if (lane < nb) {
-            const uint64_t key = rb.keys[(size_t)i * kRoundBlocks + lane];
-            uint64_t slot = slot_home(key, mdl, t.req_mask);
-            for (;;) {
-                uint4 a0, b0, a1, b1;
-                ld_slot_pair(t.req + slot, a0, b0, a1, b1);
-                if (slot_matches(a0, b0, key, mdl)) { hit = true; e0 = a0.z; e1 = a0.w; e2 = b0.x; e3 = b0.y; e4 = b0.z; cnt = meta_count(b0.w); break; }
-                if (meta_state(b0.w) == kStateEmpty) break;
-                if (slot_matches(a1, b1, key, mdl)) { hit = true; e0 = a1.z; e1 = a1.w; e2 = b1.x; e3 = b1.y; e4 = b1.z; cnt = meta_count(b1.w); break; }
-                if (meta_state(b1.w) == kStateEmpty) break;
-                slot = (slot + 2) & t.req_mask;
-            }
-        }
-        const uint32_t valid = nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u);
-        const uint32_t hitmask = __ballot_sync(0xffffffffu, hit) & valid;
-        const int nhit = __ffs(~hitmask) - 1;                 // consecutive hits from the round's first block (32 if all)
-        // ---- 2. walk state: lane q owns block-0 pod q ----
+__global__ void __launch_bounds__(kProbeThreads, 4)
+probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+    extern __shared__ __align__(16) unsigned char smem_raw_w[];
+    WalkSmem& sm = *reinterpret_cast<WalkSmem*>(smem_raw_w);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WalkSmem::Warp& W = sm.w[wid];
+    if (threadIdx.x < 16) sm.weight[threadIdx.x] = t.weight[threadIdx.x];
+    __syncthreads();
+    const unsigned int n_act = rb.n_act[cur];
+    const size_t kstride = (size_t)a.n_prompts;
+    const unsigned int total_warps = gridDim.x * (kProbeThreads / 32);
+    for (unsigned int w = blockIdx.x * (kProbeThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
+        const unsigned int i = w * 32u + lane;
+        const bool have = i < n_act;
+        const uint32_t p = have ? rb.act[cur][i] : 0u;
+        const uint32_t meta = have ? rb.nbr[i] : 0u;
+        const int nb = (int)(meta & 63u);
+        const bool has_more = (meta >> 8) & 1u;
+        const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
         uint32_t k = 0, alive = 0;
-        uint32_t mypod = 0xffffffffu; double mysc = 0.0;
-        int start = 0;                                        // first block of this round still to be scored
-        if (round == 0) {
-            if (nhit > 0) {
-                // activePods := pods of block 0 after the filter; score = max weight      (kvblock_scorer.go:118-128)
-                const uint32_t f0 = __shfl_sync(0xffffffffu, e0, 0), f1 = __shfl_sync(0xffffffffu, e1, 0), f2 = __shfl_sync(0xffffffffu, e2, 0),
-                               f3 = __shfl_sync(0xffffffffu, e3, 0), f4 = __shfl_sync(0xffffffffu, e4, 0), fc = __shfl_sync(0xffffffffu, cnt, 0);
-                const uint64_t* frow = filter_row(a.filter, p, t.filter_words);
-                const uint32_t myent = lane < (int)fc ? ent_of(f0, f1, f2, f3, f4, lane) : 0u;
-                const bool pass = lane < (int)fc && (!frow || filter_has(frow, myent >> 4));
-                bool firstocc = pass;                          // first passing occurrence of this pod id in the slot
-                for (int j = 0; j < kMaxEnt; ++j) {
-                    const uint32_t oe = __shfl_sync(0xffffffffu, myent, j);
-                    const bool op = __shfl_sync(0xffffffffu, (int)pass, j);
-                    if (j < lane && op && (oe >> 4) == (myent >> 4)) firstocc = false;
-                }
-                const uint32_t fm = __ballot_sync(0xffffffffu, firstocc);
-                k = __popc(fm);
-                const int srcl = lane < (int)k ? __fns(fm, 0, lane + 1) : 0;
-                const uint32_t pe = __shfl_sync(0xffffffffu, myent, srcl);
-                if (lane < (int)k) {
-                    mypod = pe >> 4;
-                    double mx = 0.0;
-                    for (int j = 0; j < (int)fc; ++j) {
-                        const uint32_t ee = ent_of(f0, f1, f2, f3, f4, j);
-                        if ((ee >> 4) == mypod) { const double wt = s_weight[ee & 15u]; if (wt > mx) mx = wt; }
-                    }
-                    mysc = mx;
-                }
-                alive = (1u << k) - 1u;
-                start = 1;
-            }
-        } else {
+        uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0;      // last scored pattern
+        if (round > 0 && have) {
             const PromptState& ps = rb.pst[p];
             k = ps.k; alive = ps.alive;
-            if (lane < (int)k) { mypod = ps.pod[lane]; mysc = ps.sc[lane]; }
+            pv0 = ps.pat[0]; pv1 = ps.pat[1]; pv2 = ps.pat[2]; pv3 = ps.pat[3]; pv4 = ps.pat[4]; pvc = ps.pat[5];
+            for (uint32_t q = 0; q < k; ++q) { W.sc[q][lane] = ps.sc[q]; W.pod[q][lane] = ps.pod[q]; W.bt[q][lane] = ps.bt[q]; }
         }
-        // ---- 3. blocks [start, nhit): activePods &= pods(block); score += max weight, in block order (kvblock_scorer.go:130-147)
-        //         consecutive blocks with bitwise-equal entry words form a run: one scan, then `len` ordered adds.
-        {
-            const uint32_t pe0 = __shfl_up_sync(0xffffffffu, e0, 1), pe1 = __shfl_up_sync(0xffffffffu, e1, 1), pe2 = __shfl_up_sync(0xffffffffu, e2, 1),
-                           pe3 = __shfl_up_sync(0xffffffffu, e3, 1), pe4 = __shfl_up_sync(0xffffffffu, e4, 1), pc = __shfl_up_sync(0xffffffffu, cnt, 1);
-            const bool same_as_prev = lane > 0 && (((pe0 ^ e0) | (pe1 ^ e1) | (pe2 ^ e2) | (pe3 ^ e3) | (pe4 ^ e4) | (pc ^ cnt)) == 0u);
-            const uint32_t samemask = __ballot_sync(0xffffffffu, same_as_prev);
-            int b = start;
-            while (b < nhit && alive) {
-                // run [b, e): block b plus the following blocks whose pattern equals their predecessor's
-                const uint32_t follow = (samemask >> (b + 1 < 32 ? b + 1 : 31)) ;
-                int len = 1;
-                if (b + 1 < 32) len += __ffs(~follow) - 1;
-                if (b + len > nhit) len = nhit - b;
-                const uint32_t r0 = __shfl_sync(0xffffffffu, e0, b), r1 = __shfl_sync(0xffffffffu, e1, b), r2 = __shfl_sync(0xffffffffu, e2, b),
-                               r3 = __shfl_sync(0xffffffffu, e3, b), r4 = __shfl_sync(0xffffffffu, e4, b), rc = __shfl_sync(0xffffffffu, cnt, b);
-                bool present = false; double mx = 0.0;
-                if (lane < (int)k && ((alive >> lane) & 1u)) {
-                    for (int j = 0; j < (int)rc; ++j) {
-                        const uint32_t ee = ent_of(r0, r1, r2, r3, r4, j);
-                        if ((ee >> 4) == mypod) { present = true; const double wt = s_weight[ee & 15u]; if (wt > mx) mx = wt; }
+        const uint64_t* frow = nullptr;
+        const int nb_max = __reduce_max_sync(0xffffffffu, nb);
+        bool done = !have || nb == 0;                          // walk ended (miss / no live pod); scores are final
+        // slot pair of block 0
+        // (An L2 prefetch running 8 blocks ahead of the walk was tried and made this kernel 2x slower -- DRAM reads
+        //  grew 50 % and issue utilisation fell to 11 %; profiles/r1d_*.  The SM's outstanding-miss capacity, not the
+        //  DRAM latency of a single chain, is what bounds it; the batch is sorted by prefix instead so that lanes of
+        //  a warp ask for the same slots.)
+        uint64_t key = 0, slot = 0;
+        uint4 A0 = {0, 0, 0, 0}, B0 = {0, 0, 0, 0}, A1 = {0, 0, 0, 0}, B1 = {0, 0, 0, 0};
+        if (!done) {
+            key = rb.keys[i];
+            slot = slot_home(key, mdl, t.req_mask);
+            ld_slot_pair(t.req + slot, A0, B0, A1, B1);
+        }
+        uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + i] : 0ull;                         // key of block j+1
+        for (int j = 0; j < nb_max; ++j) {
+            // next block's pair is requested before this block is scored; keys are read one iteration ahead of their use
+            uint64_t nkey = key1, nslot = 0;
+            uint4 nA0 = {0, 0, 0, 0}, nB0 = {0, 0, 0, 0}, nA1 = {0, 0, 0, 0}, nB1 = {0, 0, 0, 0};
+            const bool nextv = !done && (j + 1 < nb);
+            if (nextv) {
+                nslot = slot_home(nkey, mdl, t.req_mask);
+                ld_slot_pair(t.req + nslot, nA0, nB0, nA1, nB1);
+            }
+            key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + i] : 0ull;
+            if (!done && j < nb) {
+                uint4 A = A0, B = B0;
+                bool hit = slot_matches(A, B, key, mdl);
+                if (!hit && meta_state(B.w) != kStateEmpty) {
+                    A = A1; B = B1;
+                    hit = slot_matches(A, B, key, mdl);
+                    while (!hit && meta_state(B.w) != kStateEmpty) {          // rare: displaced past the home pair
+                        slot = (slot + 2) & t.req_mask;
+                        ld_slot_pair(t.req + slot, A0, B0, A1, B1);
+                        A = A0; B = B0; hit = slot_matches(A, B, key, mdl);
+                        if (!hit && meta_state(B.w) != kStateEmpty) { A = A1; B = B1; hit = slot_matches(A, B, key, mdl); }
                     }
-                    if (present) for (int x = 0; x < len; ++x) mysc = __dadd_rn(mysc, mx);
                 }
-                alive &= __ballot_sync(0xffffffffu, present);
-                b += len;
+                if (!hit) { done = true; }
+                else {
+                    SlotWords sw; sw.a = A; sw.b = B;
+                    const uint32_t cnt = meta_count(B.w);
+                    const bool first_block = (round == 0 && j == 0);
+                    const bool same = !first_block && (((pv0 ^ A.z) | (pv1 ^ A.w) | (pv2 ^ B.x) | (pv3 ^ B.y) | (pv4 ^ B.z) | (pvc ^ cnt)) == 0u);
+                    if (same) {
+                        uint32_t am = alive;
+                        while (am) {
+                            const int q = __ffs(am) - 1; am &= am - 1;
+                            const uint32_t bt = W.bt[q][lane];
+                            const double mx = bt == 0xffu ? 0.0 : sm.weight[bt];
+                            W.sc[q][lane] = __dadd_rn(W.sc[q][lane], mx);
+                        }
+                    } else if (first_block) {
+                        // activePods := pods of block 0 (after the filter); score = max weight   (kvblock_scorer.go:118-128)
+                        frow = filter_row(a.filter, p, t.filter_words);
+                        k = 0;
+                        for (uint32_t e = 0; e < cnt; ++e) {
+                            const uint32_t pt = slot_ent(sw, e), pd = pt >> 4;
+                            if (frow && !filter_has(frow, pd)) continue;
+                            const double wt = sm.weight[pt & 15u];
+                            uint32_t q = 0;
+                            for (; q < k; ++q) if (W.pod[q][lane] == pd) break;
+                            if (q == k) { W.pod[k][lane] = (uint16_t)pd; W.sc[k][lane] = 0.0; W.bt[k][lane] = 0xffu; ++k; }
+                            if (wt > W.sc[q][lane]) { W.sc[q][lane] = wt; W.bt[q][lane] = (uint8_t)(pt & 15u); }
+                        }
+                        alive = (1u << k) - 1u;
+                    } else {
+                        // activePods &= pods(block); score[p] += max weight, in block order   (kvblock_scorer.go:130-147)
+                        uint32_t am = alive;
+                        while (am) {
+                            const int q = __ffs(am) - 1; am &= am - 1;
+                            const uint32_t want = W.pod[q][lane];
+                            double mx = 0.0; bool present = false; uint32_t bt = 0xffu;
+                            for (uint32_t e = 0; e < cnt; ++e) {
+                                const uint32_t pt = slot_ent(sw, e);
+                                if ((pt >> 4) == want) { present = true; const double wt = sm.weight[pt & 15u]; if (wt > mx) { mx = wt; bt = pt & 15u; } }
+                            }
+                            if (present) { W.sc[q][lane] = __dadd_rn(W.sc[q][lane], mx); W.bt[q][lane] = (uint8_t)bt; }
+                            else alive &= ~(1u << q);
+                        }
+                    }
+                    pv0 = A.z; pv1 = A.w; pv2 = B.x; pv3 = B.y; pv4 = B.z; pvc = cnt;
+                    if (!alive) done = true;
+                }
+            }
+            key = nkey; slot = nslot; A0 = nA0; B0 = nB0; A1 = nA1; B1 = nB1;
+        }
+        // ---- continue next round, or write the result ----
+        const bool more = have && !done && has_more;           // all blocks of the round hit, pods still live, blocks left
+        const uint32_t mm = __ballot_sync(0xffffffffu, more);
+        if (mm) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (more) {
+                rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
+                PromptState& ps = rb.pst[p];
+                ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
+                ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
+                for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; ps.bt[q] = W.bt[q][lane]; }
             }
         }
-        // ---- 4. finished, or continue next round ----
-        const bool more = alive != 0 && nhit == nb && nb == kRoundBlocks && first + nb < nblk;
-        if (more) {
-            PromptState& ps = rb.pst[p];
-            if (lane < (int)k) { ps.pod[lane] = (uint16_t)mypod; ps.sc[lane] = mysc; }
-            if (lane == 0) { ps.k = (uint8_t)k; ps.alive = (uint16_t)alive; rb.act[cur ^ 1][atomicAdd(&rb.n_act[cur ^ 1], 1u)] = p; }
-        } else {
+        __syncwarp();
+        uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
+        while (dm) {                                           // the whole warp writes each finished prompt's row
+            const int l = __ffs(dm) - 1; dm &= dm - 1;
+            const uint32_t pp = __shfl_sync(0xffffffffu, p, l);
+            const uint32_t pk = __shfl_sync(0xffffffffu, k, l);
+            const uint32_t pmeta = __shfl_sync(0xffffffffu, meta, l);
             if (a.dense) {
-                double* row = a.dense + (long long)p * t.max_pods;
+                double* row = a.dense + (long long)pp * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
                     for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
@@ -254,32 +316,47 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                 }
                 __syncwarp();
-                if (lane < (int)k && mypod < P) row[mypod] = mysc;
+                if ((uint32_t)lane < pk) { const uint32_t pd = W.pod[lane][l]; if (pd < P) row[pd] = W.sc[lane][l]; }
             }
             if (a.sp_cnt) {
-                if (lane < (int)k) { a.sp_pods[(long long)p * kMaxEnt + lane] = (uint16_t)mypod; a.sp_scores[(long long)p * kMaxEnt + lane] = mysc; }
-                if (lane == 0) a.sp_cnt[p] = (uint8_t)k;
+                if ((uint32_t)lane < pk) { a.sp_pods[(long long)pp * kMaxEnt + lane] = W.pod[lane][l]; a.sp_scores[(long long)pp * kMaxEnt + lane] = W.sc[lane][l]; }
+                if (lane == 0) a.sp_cnt[pp] = (uint8_t)pk;
             }
-            if (a.has_keys && lane == 0) a.has_keys[p] = nblk > 0;
+            if (a.has_keys && lane == 0) a.has_keys[pp] = (round > 0) || (pmeta & 63u) > 0;
         }
         __syncwarp();
     }
 }
 
-__global__ void rounds_init_kernel(const ScoreArgs a, const RoundBufs rb, uint32_t block_size, unsigned long long* max_blocks) {
+// List setup + a 64-bit fingerprint of every prompt's first block.  The batch is then radix-sorted by fingerprint so
+// that prompts sharing a prefix sit in neighbouring lanes: their probes are the same 64-byte segments, which the
+// load unit merges within a warp and L2 serves across warps.  (Any order gives the same results; this one lets the
+// prefix sharing the system exists for -- system prompts, shared documents -- show up as memory locality.)
+__global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsigned long long* max_blocks, uint64_t* fp, uint32_t* idx,
+                                   unsigned int* n_act, unsigned int n_first) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned long long nb = 0;
     if (i < a.n_prompts) {
-        rb.act[0][i] = (uint32_t)i;
-        nb = (unsigned long long)((a.tok_off[i + 1] - a.tok_off[i]) / block_size);
+        const int64_t b = a.tok_off[i] - a.tok_base, e = a.tok_off[i + 1] - a.tok_base;
+        nb = (unsigned long long)((e - b) / block_size);
+        uint64_t f = ~0ull;                                   // prompts without a full block sort last
+        if (nb > 0) {
+            f = 0x9E3779B97F4A7C15ull;
+            const uint32_t* tk = a.tok + b;
+            for (uint32_t j = 0; j < block_size && j < 16u; ++j) f = mix64(f ^ __ldg(tk + j));
+            f &= ~(1ull << 63);
+        }
+        fp[i] = f; idx[i] = (uint32_t)i;
     }
     nb = __reduce_max_sync(0xffffffffu, (unsigned)min(nb, 0xffffffffull));
     if ((threadIdx.x & 31) == 0 && nb) atomicMax(max_blocks, nb);
-    if (i == 0) { rb.n_act[0] = (unsigned int)a.n_prompts; rb.n_act[1] = 0; }
+    if (i == 0) { n_act[0] = n_first; n_act[1] = 0; n_act[2] = (unsigned int)a.n_prompts - n_first; n_act[3] = 0; }
 }
 
 inline int rounds_init() {
-    return cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) == cudaSuccess ? 0 : -1;
+    if (cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(probe_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)) != cudaSuccess) return -1;
+    return 0;
 }
 
 }  // namespace kvx

@@ -15,6 +15,7 @@
 #include "kernels_write.cuh"
 #include "kernels_score.cuh"
 #include "kernels_rounds.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 using namespace kvx;
 
@@ -94,7 +95,11 @@ struct kvidx {
     int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
-    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst;
+    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort;
+    int sort_prefix = 1;           // sort the batch by first-block fingerprint before the rounds
+    int rounds_overlap = 1;        // run the two halves of a large batch on two streams
+    int64_t rounds_overlap_min = 65536;
+    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -152,21 +157,42 @@ int ensure_room(kvidx* x, uint64_t incoming) {
 struct ScoreOut { double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* sp_cnt; uint8_t* has_keys; };
 
 // Large batches: alternating hash / probe rounds (kernels_rounds.cuh).  max_blocks < 0: computed on the device.
+// The sorted batch is split into two halves that run their rounds on two streams, so the compute-bound hash kernel
+// of one half shares the SMs with the memory-bound walk kernel of the other.
 int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
                         const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
                         int64_t max_blocks) {
     CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(64));
     CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState)));
-    RoundBufs rb{};
-    rb.act[0] = x->r_act0.as<uint32_t>(); rb.act[1] = x->r_act1.as<uint32_t>();
-    rb.n_act = x->r_cnt.as<unsigned int>();
+    CK(x->r_nbr.need((size_t)n * 4));
+    const bool overlap = x->rounds_overlap && n >= x->rounds_overlap_min;
+    const int64_t nA = overlap ? ((n / 2 + 31) & ~31ll) : n, nB = n - nA;
+    unsigned int* cnt = x->r_cnt.as<unsigned int>();
     unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(x->r_cnt.as<unsigned char>() + 16);
-    rb.hstate = x->r_hstate.as<uint64_t>(); rb.keys = x->r_keys.as<uint64_t>(); rb.pst = x->r_pst.as<PromptState>();
+    RoundBufs rb[2]{};
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        const int64_t off = hlf ? nA : 0;
+        rb[hlf].act[0] = x->r_act0.as<uint32_t>() + off; rb[hlf].act[1] = x->r_act1.as<uint32_t>() + off;
+        rb[hlf].n_act = cnt + 2 * hlf;
+        rb[hlf].hstate = x->r_hstate.as<uint64_t>(); rb[hlf].pst = x->r_pst.as<PromptState>();
+        rb[hlf].keys = x->r_keys.as<uint64_t>() + off; rb[hlf].nbr = x->r_nbr.as<uint32_t>() + off;
+    }
     ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
     CK(cudaMemsetAsync(x->r_cnt.p, 0, 64, st));
-    rounds_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, rb, x->tv.block_size, d_maxb);
+    CK(x->r_fp.need((size_t)n * 8 * 2 + (size_t)n * 4));
+    uint64_t* fp_in = x->r_fp.as<uint64_t>(); uint64_t* fp_out = fp_in + n;
+    uint32_t* idx_in = reinterpret_cast<uint32_t*>(fp_out + n);
+    rounds_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, x->tv.block_size, d_maxb, fp_in, x->sort_prefix ? idx_in : rb[0].act[0], cnt,
+                                                                    (unsigned int)nA);
     x->launches += 1;
     CK(cudaGetLastError());
+    if (x->sort_prefix) {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
+        CK(x->r_sort.need(tmp));
+        CK(cub::DeviceRadixSort::SortPairs(x->r_sort.p, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
+        x->launches += 6;     // cub: histogram + onesweep passes
+    }
     if (max_blocks < 0) {
         unsigned long long mb = 0;
         CK(cudaMemcpyAsync(&mb, d_maxb, sizeof mb, cudaMemcpyDeviceToHost, st));
@@ -175,15 +201,26 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
     }
     int64_t rounds = (max_blocks + kRoundBlocks - 1) / kRoundBlocks;
     if (rounds < 1) rounds = 1;                       // round 0 also retires the prompts that have no full block
-    const unsigned hgrid = (unsigned)std::min<int64_t>((n + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * 4);
-    const unsigned pgrid = (unsigned)std::min<int64_t>((n * 32 + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * 8);
+    cudaStream_t strm[2] = {st, x->aux_stream};
+    const int nh = nB > 0 ? 2 : 1;
+    if (nh == 2) { CK(cudaEventRecord(x->ev_fork, st)); CK(cudaStreamWaitEvent(x->aux_stream, x->ev_fork, 0)); }
+    const int per_sm_h = nh == 2 ? 2 : 4, per_sm_p = nh == 2 ? 2 : 4;
     for (int64_t r = 0; r < rounds; ++r) {
         const int cur = (int)(r & 1);
-        hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), st>>>(x->tv, a, rb, cur, (int)r);
-        probe_round_kernel<<<pgrid, kProbeThreads, 0, st>>>(x->tv, a, rb, cur, (int)r);
-        x->launches += 2;
+        for (int hlf = 0; hlf < nh; ++hlf) {
+            const int64_t m = hlf ? nB : nA;
+            const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * per_sm_h);
+            hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+        }
+        for (int hlf = 0; hlf < nh; ++hlf) {
+            const int64_t m = hlf ? nB : nA;
+            const unsigned pgrid = (unsigned)std::min<int64_t>((m + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * per_sm_p);
+            probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+        }
+        x->launches += 2 * nh;
     }
     CK(cudaGetLastError());
+    if (nh == 2) { CK(cudaEventRecord(x->ev_join, x->aux_stream)); CK(cudaStreamWaitEvent(st, x->ev_join, 0)); }
     return 0;
 }
 
@@ -418,6 +455,9 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     CK(cudaStreamCreateWithFlags(&x->own_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&x->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming));
     x->stream = x->own_stream;
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
@@ -443,6 +483,9 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
     if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : 0;
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
+    if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
     if (rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = score_tuned_init();
     if (rc) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -461,7 +504,7 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_done[i]) cudaEventDestroy(x->ev_done[i]);
         if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]);
     }
-    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release();
+    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release();
     x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
     if (x->tv.req) cudaFree(x->tv.req);
     if (x->tv.eng) cudaFree(x->tv.eng);
@@ -471,6 +514,9 @@ void kvidx_destroy(kvidx_t* x) {
     if (x->own_stream) cudaStreamDestroy(x->own_stream);
     if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
     if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
+    if (x->aux_stream) cudaStreamDestroy(x->aux_stream);
+    if (x->ev_fork) cudaEventDestroy(x->ev_fork);
+    if (x->ev_join) cudaEventDestroy(x->ev_join);
     delete x;
 }
 

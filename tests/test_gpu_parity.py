@@ -266,14 +266,22 @@ def test_batched_events_per_pod_order_vs_oracle():
 
 
 def _select_path(monkeypatch, path):
-    """v1: thread-per-prompt kernel; fused: persistent lane-worker kernel; rounds: hash/probe round pipeline."""
+    """v1: thread-per-prompt kernel; fused: persistent lane-worker kernel; rounds: hash/probe round pipeline
+    (one stream); rounds2: the same with the batch split over two streams; rounds-nosort: without the prefix sort."""
     if path == "v1":
         monkeypatch.setenv("KVIDX_SCORE_KERNEL", "v1")
+    elif path == "rounds2":
+        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
+        monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP_MIN", "64")
+    elif path == "rounds-nosort":
+        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
+        monkeypatch.setenv("KVIDX_SORT_PREFIX", "0")
     else:
         monkeypatch.setenv("KVIDX_SCORE_PATH", path)
+        monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP", "0")
 
 
-PATHS = ["v1", "fused", "rounds"]
+PATHS = ["v1", "fused", "rounds", "rounds2", "rounds-nosort"]
 
 
 @pytest.mark.parametrize("kernel", PATHS)
@@ -297,7 +305,7 @@ def test_synth_config2_shape_vs_oracle_and_closed_form(kernel, monkeypatch):
     assert np.array_equal(s1, wl.expected_scores(doc, m))
 
 
-@pytest.mark.parametrize("kernel", ["fused", "rounds"])
+@pytest.mark.parametrize("kernel", ["fused", "rounds", "rounds2", "rounds-nosort"])
 def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
     """Lane refill / round lists, unaligned prompt starts (per-lane staging fallback), empty and sub-block
     prompts, pod filters, against the oracle."""
