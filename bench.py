@@ -146,9 +146,10 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the score kernel from the committed ncu summary, if present."""
+    """DRAM bytes (read+write) per prompt of one Score() step, summed over its kernels, from the committed ncu
+    capture (profiles/score_step_traffic.json); None if no capture is committed."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "score_kernel_traffic.json")))["dram_bytes_per_launch_per_prompt"]
+        return json.load(open(os.path.join(ROOT, "profiles", "score_step_traffic.json")))["dram_bytes_per_prompt"]
     except Exception:
         return None
 
@@ -253,8 +254,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     wl = synth.Workload(CONFIG_ID, T_TOKENS, N_BLOCKS, N_PODS, BLOCK)
-    Q = int(os.environ.get("KVIDX_BENCH_BATCH", str(262144)))      # prompts resident in HBM per step (per GPU)
-    QE = int(os.environ.get("KVIDX_BENCH_E2E_BATCH", str(32768)))  # prompts per e2e step (host buffers)
+    Q = int(os.environ.get("KVIDX_BENCH_BATCH", str(524288)))      # prompts resident in HBM per step (per GPU)
+    QE = int(os.environ.get("KVIDX_BENCH_E2E_BATCH", str(65536)))  # prompts per e2e step (host buffers)
 
     # ---- index: filled through the write path (BlockStored events), every rank holds a full replica ----
     ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + 1024, max_pods=wl.P, tier_weights=WEIGHTS, device=local)
@@ -321,6 +322,19 @@ def run_ours(args):
         total_ms = float(tt.item())
     value = world * Q * args.steps / (total_ms / 1e3)
 
+    # the SURVEY's "64K batch" regime on the same resident data (fewer chains in flight, less prefix sharing per batch)
+    q64 = min(Q, 65536)
+    def step64():
+        ix.score_batch_dev(d_tok.data_ptr(), d_off.data_ptr(), q64, d_scores.data_ptr(), d_has_keys=d_has.data_ptr())
+    for _ in range(3):
+        step64()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); e0.record(stream)
+    for _ in range(5):
+        step64()
+    e1.record(stream); barrier()
+    value_64k = world * q64 * 5 / (e0.elapsed_time(e1) / 1e3)
+
     # roofline of the dominant (only) kernel in the step
     A = algorithmic_bytes(wl, m)
     peak, peak_src = measured_peak()
@@ -331,7 +345,10 @@ def run_ours(args):
             "traffic": None if traffic is None else traffic * Q,
             "peak_source": peak_src, "algorithmic_bytes_per_prompt_mean": float(A.mean()),
             "algorithmic_bytes_per_launch": float(A.sum()), "kernel_ms": float(step_ms.mean()),
-            "note": "FNV-1a chain is serial per prompt: integer-issue bound sits near the HBM bound (DESIGN.md)"}
+            "kernel": "one step = prefix sort + 8 x (hash_round_kernel, probe_round_kernel); achieved = step's algorithmic bytes / "
+                      "step GPU time (CUDA events around all of its launches), i.e. a lower bound for every kernel in it",
+            "note": "co-limited: FNV-1a issue bound (4.2e10 block-hashes/s measured, scripts/ubench_hash.cu) and the HBM random-access "
+                    "rate (36 G 64-byte reads/s measured, scripts/ubench_mem.cu); see DESIGN.md"}
 
     # ---- e2e: host pinned buffers through kvidx_score_batch (H2D + kernel + D2H inside the timed region) ----
     ix.set_stream(0)
@@ -393,10 +410,11 @@ def run_ours(args):
                "config": {"workload": "Score() 4096-token prompts, 10M-block / 256-pod index (SURVEY 8(d) metric row)",
                           "prompt_tokens": wl.T, "index_blocks": wl.n_blocks, "pods": wl.P, "block_size": BLOCK,
                           "batch_prompts_per_gpu": Q, "query_mix": "m uniform in [0,n] matched blocks + random tail",
+                          "queries_per_document": Q / wl.D,
                           "l2_policy": "inputs (%.1f GB tokens + %.1f GB table) larger than the 126 MB L2; no flush" % (Q * wl.T * 4 / 1e9, st["request_slots"] * 32 / 1e9),
                           "multi_gpu": "replicas: full index per GPU, prompts sharded, no data-path collective" if world > 1 else "single GPU",
                           "index_fill_s": fill_s, "fill_events": n_ev},
-               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat,
+               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k,
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -268,8 +268,10 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
     const uint32_t P = x->tv.max_pods, FW = x->tv.filter_words;
     const bool sparse = sp_cnt != nullptr;
     const size_t out_row = sparse ? (size_t)kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 2 : (size_t)P * sizeof(double) + 1;
-    const int64_t kMaxTokChunk = 8ll << 20;       // tokens per chunk (32 MiB): small enough to pipeline, large enough for DMA
-    const int64_t kMaxRowsChunk = std::max<int64_t>(1, (32ll << 20) / (int64_t)out_row);
+    // chunk = up to 32 Mi tokens (128 MiB): the H2D copy of a chunk (2.3 ms at 55 GB/s) must outlast its kernel
+    // (~1 ms for 8192 x 4K-token prompts) for the pipeline to be PCIe bound; 8 Mi-token chunks were kernel bound.
+    const int64_t kMaxTokChunk = 32ll << 20;
+    const int64_t kMaxRowsChunk = std::max<int64_t>(1, (128ll << 20) / (int64_t)out_row);
     const bool tok_pinned = tok && is_device_accessible_host(tok);
     const bool out_pinned = !sparse && dense && is_device_accessible_host(dense) && (!has_keys || is_device_accessible_host(has_keys));
     cudaStream_t s_k = x->stream, s_in = x->copy_stream, s_out = x->d2h_stream;

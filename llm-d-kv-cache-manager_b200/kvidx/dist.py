@@ -1,0 +1,79 @@
+"""One-process-per-GPU plumbing for the replica mode (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+
+The Score() path shards by prompt: every rank holds a full replica of the index (10 M blocks = 1 GB of slots),
+scores its own contiguous slice of the batch, and no data-path collective is needed.  What has to be replicated is
+the write path: every rank must apply the same KV events, in the same per-pod order.  `broadcast_event_batch` does
+that from the ingesting rank; `shard_range` splits a batch; `max_over_ranks` is the timing reduction bench.py uses.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+EVENT_DTYPE = np.dtype([("op", "u1"), ("has_parent", "u1"), ("podtier", "<u2"), ("model", "<u4"),
+                        ("parent_hash", "<u8"), ("hash_off", "<u8"), ("tok_off", "<u8"),
+                        ("n_hashes", "<u4"), ("n_tokens", "<u4")])
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced split of n prompts: ranks [0, n % world) get one extra."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Device-timed milliseconds -> max over ranks (the number a multi-GPU step is judged by)."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def broadcast_event_batch(events, hashes, tokens, src: int = 0, device=None):
+    """Replicate one decoded event batch (kvidx_event_t array + flat hash / token arrays) from `src` to all ranks.
+    Returns numpy arrays on every rank.  Sizes go first, then the three payloads as byte tensors."""
+    rank = dist.get_rank()
+    if rank == src:
+        ev = np.ascontiguousarray(events, EVENT_DTYPE)
+        hs = np.ascontiguousarray(hashes, np.uint64)
+        tk = np.ascontiguousarray(tokens, np.uint32)
+        sizes = torch.tensor([len(ev), len(hs), len(tk)], dtype=torch.int64, device=device)
+    else:
+        sizes = torch.zeros(3, dtype=torch.int64, device=device)
+    dist.broadcast(sizes, src)
+    n_ev, n_hs, n_tk = (int(v) for v in sizes.tolist())
+    out = []
+    for arr, n, dt in ((events, n_ev, EVENT_DTYPE), (hashes, n_hs, np.dtype(np.uint64)), (tokens, n_tk, np.dtype(np.uint32))):
+        nbytes = n * dt.itemsize
+        if rank == src:
+            buf = torch.from_numpy(np.ascontiguousarray(arr, dt).view(np.uint8).reshape(-1).copy())
+        else:
+            buf = torch.empty(nbytes, dtype=torch.uint8)
+        if device is not None:
+            buf = buf.to(device)
+        if nbytes:
+            dist.broadcast(buf, src)
+        out.append(buf.cpu().numpy().view(dt) if nbytes else np.zeros(0, dt))
+    return tuple(out)
+
+
+def gather_scores(local_scores: np.ndarray, n_total: int, device=None):
+    """Collect the per-rank score slices (shard_range order) on every rank (all_gather of padded rows)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    P = local_scores.shape[1]
+    cap = -(-n_total // world)
+    pad = np.full((cap, P), -1.0)
+    pad[: len(local_scores)] = local_scores
+    t = torch.from_numpy(pad)
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    out = np.empty((n_total, P))
+    for r in range(world):
+        lo, hi = shard_range(n_total, r, world)
+        out[lo:hi] = parts[r].cpu().numpy()[: hi - lo]
+    return out

@@ -1,0 +1,71 @@
+"""CPU, world_size 2, gloo: the replica-mode plumbing (prompt sharding, event replication, max-over-ranks timing).
+The index on each rank is the C++ oracle here (no GPU in this container); on the GPU box the same helpers carry
+libkvidx handles (bench.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from kvidx import dist as kd
+from kvidx import synth
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.kvoracle_c import COracle
+        wl = synth.Workload(3, 512, 1 << 11, 16)
+        co = COracle(size=10 ** 6, max_pods=16)
+        # rank 0 ingests the events, every rank applies the replicated batch
+        ev, hs, tk = wl.fill_events(0, wl.D) if rank == 0 else (None, None, None)
+        ev, hs, tk = kd.broadcast_event_batch(ev, hs, tk, src=0)
+        assert co.apply_events(ev, hs, tk) == (0, 0)
+        assert co.len_request() == wl.n_blocks
+        # prompts are sharded; each rank scores its slice; the gathered result equals the single-rank result
+        n = 203
+        toks, doc, m = wl.queries(0, n)
+        lo, hi = kd.shard_range(n, rank, world)
+        off = np.arange(0, (hi - lo + 1) * wl.T, wl.T, dtype=np.int64)
+        local, _, _, _ = co.score_batch(toks[lo:hi].reshape(-1), off)
+        full = kd.gather_scores(local, n)
+        assert np.array_equal(full, wl.expected_scores(doc, m))
+        # timing reduction: max over ranks
+        assert kd.max_over_ranks(10.0 + rank) == 10.0 + world - 1
+        q.put((rank, lo, hi, True))
+    except Exception as e:      # noqa: BLE001
+        q.put((rank, -1, -1, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 64, 203, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [kd.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_replica_mode_two_ranks_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[3] is True for r in res), res
+    spans = sorted((r[1], r[2]) for r in res)
+    assert spans == [(0, 102), (102, 203)]
