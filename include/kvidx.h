@@ -82,7 +82,10 @@ typedef struct kvidx_config {
     uint32_t lru_exact;        /* 1: track key recency so that Size-cap eviction is exact LRU
                                   (in_memory.go:59,118,170); 0: recency not tracked, inserting
                                   beyond `capacity` fails with KVIDX_ENOSPC                      */
-    uint32_t reserved[7];
+    uint32_t shard_rank;       /* hash-range sharding over the GPUs of one NVSwitch domain: this handle */
+    uint32_t shard_count;      /* owns shard `shard_rank` of `shard_count` (power of two <= 8; 0 or 1 = unsharded).   */
+                               /* `capacity` stays the TOTAL key budget; each shard holds capacity/shard_count.        */
+    uint32_t reserved[5];
 } kvidx_config_t;
 
 void        kvidx_config_default(kvidx_config_t* cfg);
@@ -192,6 +195,19 @@ int kvidx_hash_keys_dev(kvidx_t* idx, const uint32_t* d_tok, const int64_t* d_to
 int kvidx_apply_events_dev(kvidx_t* idx, const kvidx_event_t* d_ev_sorted, const int64_t* d_queue_off,
                            int64_t n_queues, const uint64_t* d_hashes, const uint32_t* d_tokens,
                            int64_t* d_n_dropped);
+
+/* ---- hash-range sharding across GPUs (one process per GPU) ------------------------
+ * The request and engine tables are partitioned by the top bits of the mixed key.  Every rank maps its peers'
+ * shards (CUDA IPC over NVLink / NVSwitch peer memory) and the SAME kernels then probe, lock and update slots
+ * wherever they live: a Score() probe of a remote key is a 64-byte peer load issued from the fused walk, an
+ * Add / Evict is a system-scope CAS on the owner's slot.  No collective sits on the data path; NCCL (or any
+ * transport) is only needed to exchange the 192-byte handle blobs once.
+ * Ingest rule: all events of one pod must be applied through ONE rank (per-pod order, kvevents/pool.go:129-144). */
+#define KVIDX_SHARD_HANDLE_BYTES 192
+int kvidx_shard_export(kvidx_t* idx, void* handle_out /* KVIDX_SHARD_HANDLE_BYTES */);
+int kvidx_shard_import(kvidx_t* idx, uint32_t rank, const void* handle /* from that rank's kvidx_shard_export */);
+/* same-process variant (several GPUs driven by one process, e.g. tests): map `other`'s shard directly */
+int kvidx_shard_attach(kvidx_t* idx, uint32_t rank, kvidx_t* other);
 
 /* ---- introspection ------------------------------------------------------------ */
 typedef struct kvidx_stats {

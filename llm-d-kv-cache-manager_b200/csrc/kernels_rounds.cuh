@@ -142,11 +142,9 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
 }
 
 // ---- kernel P ---------------------------------------------------------------------------------
-__device__ __forceinline__ void ld_slot_pair(const ReqSlot* s, uint4& a0, uint4& b0, uint4& a1, uint4& b1) {
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w), "=r"(b0.x), "=r"(b0.y), "=r"(b0.z), "=r"(b0.w) : "l"(s));
-    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w), "=r"(b1.x), "=r"(b1.y), "=r"(b1.z), "=r"(b1.w) : "l"(s + 1));
+__device__ __forceinline__ void ld_slot_pair(const ReqSlot* s, bool peer, uint4& a0, uint4& b0, uint4& a1, uint4& b1) {
+    ld_slot(s, peer, a0, b0);
+    ld_slot(s + 1, peer, a1, b1);
 }
 
 // entry j (0..9) of a slot whose words live in this lane's registers
@@ -180,6 +178,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     __syncthreads();
     const unsigned int n_act = rb.n_act[cur];
     const size_t kstride = (size_t)a.n_prompts;
+    const bool peer = t.shard_bits != 0;
     const unsigned int total_warps = gridDim.x * (kProbeThreads / 32);
     for (unsigned int w = blockIdx.x * (kProbeThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
         const unsigned int i = w * 32u + lane;
@@ -206,21 +205,25 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         //  DRAM latency of a single chain, is what bounds it; the batch is sorted by prefix instead so that lanes of
         //  a warp ask for the same slots.)
         uint64_t key = 0, slot = 0;
+        const ReqSlot* base = t.req;                           // table (shard) of the current block's key
         uint4 A0 = {0, 0, 0, 0}, B0 = {0, 0, 0, 0}, A1 = {0, 0, 0, 0}, B1 = {0, 0, 0, 0};
         if (!done) {
             key = rb.keys[i];
-            slot = slot_home(key, mdl, t.req_mask);
-            ld_slot_pair(t.req + slot, A0, B0, A1, B1);
+            const uint64_t hm = home_of(key, mdl);
+            base = t.req_peer[shard_of(hm, t.shard_bits)]; slot = hm & t.req_mask & ~1ull;
+            ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
         }
         uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + i] : 0ull;                         // key of block j+1
         for (int j = 0; j < nb_max; ++j) {
             // next block's pair is requested before this block is scored; keys are read one iteration ahead of their use
             uint64_t nkey = key1, nslot = 0;
+            const ReqSlot* nbase = t.req;
             uint4 nA0 = {0, 0, 0, 0}, nB0 = {0, 0, 0, 0}, nA1 = {0, 0, 0, 0}, nB1 = {0, 0, 0, 0};
             const bool nextv = !done && (j + 1 < nb);
             if (nextv) {
-                nslot = slot_home(nkey, mdl, t.req_mask);
-                ld_slot_pair(t.req + nslot, nA0, nB0, nA1, nB1);
+                const uint64_t hm = home_of(nkey, mdl);
+                nbase = t.req_peer[shard_of(hm, t.shard_bits)]; nslot = hm & t.req_mask & ~1ull;
+                ld_slot_pair(nbase + nslot, peer, nA0, nB0, nA1, nB1);
             }
             key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + i] : 0ull;
             if (!done && j < nb) {
@@ -231,7 +234,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     hit = slot_matches(A, B, key, mdl);
                     while (!hit && meta_state(B.w) != kStateEmpty) {          // rare: displaced past the home pair
                         slot = (slot + 2) & t.req_mask;
-                        ld_slot_pair(t.req + slot, A0, B0, A1, B1);
+                        ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
                         A = A0; B = B0; hit = slot_matches(A, B, key, mdl);
                         if (!hit && meta_state(B.w) != kStateEmpty) { A = A1; B = B1; hit = slot_matches(A, B, key, mdl); }
                     }
@@ -283,7 +286,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     if (!alive) done = true;
                 }
             }
-            key = nkey; slot = nslot; A0 = nA0; B0 = nB0; A1 = nA1; B1 = nB1;
+            key = nkey; slot = nslot; base = nbase; A0 = nA0; B0 = nB0; A1 = nA1; B1 = nB1;
         }
         // ---- continue next round, or write the result ----
         const bool more = have && !done && has_more;           // all blocks of the round hit, pods still live, blocks left

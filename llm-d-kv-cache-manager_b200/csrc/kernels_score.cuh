@@ -87,6 +87,7 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
     typename SM::Warp& W = sm.w[wid];
     if (threadIdx.x < 16) sm.weight[threadIdx.x] = t.weight[threadIdx.x];
     __syncthreads();
+    const bool peer = t.shard_bits != 0;
 
     // ---- per-lane worker state ----
     long long pi = -1;                 // prompt index, -1 = no prompt
@@ -97,6 +98,7 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
     bool staged_cur = false, staged_next = false;
     uint64_t h = t.init_hash;
     bool pend = false; uint64_t pkey = 0, pslot = 0;
+    const ReqSlot* pbase = t.req;      // table (shard) the pending probe goes to
     uint4 pa0 = {0, 0, 0, 0}, pb0 = {0, 0, 0, 0}, pa1 = {0, 0, 0, 0}, pb1 = {0, 0, 0, 0};
     int pblk = 0;
     uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0;   // entry words + count of the previous block's slot
@@ -219,8 +221,8 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
                     if (!hit && !term) { A = pa1; B = pb1; hit = slot_matches(A, B, pkey, mdl); term = !hit && meta_state(B.w) == kStateEmpty; }
                     if (hit || term) break;
                     pslot = (pslot + 2) & t.req_mask;
-                    const uint4* sp = reinterpret_cast<const uint4*>(t.req + pslot);
-                    pa0 = ld_nc_v4(sp); pb0 = ld_nc_v4(sp + 1); pa1 = ld_nc_v4(sp + 2); pb1 = ld_nc_v4(sp + 3);
+                    const uint4* sp = reinterpret_cast<const uint4*>(pbase + pslot);
+                    ld_slot(reinterpret_cast<const ReqSlot*>(sp), peer, pa0, pb0); ld_slot(reinterpret_cast<const ReqSlot*>(sp) + 1, peer, pa1, pb1);
                 }
                 // leave the resolved slot in the registers: step 4 consumes it without a retry
                 if (hit) { pa0 = A; pb0 = B; } else { pb0.w = 0; }
@@ -239,8 +241,8 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
             if (!hit && !term) { A = pa1; B = pb1; hit = slot_matches(A, B, pkey, mdl); term = !hit && meta_state(B.w) == kStateEmpty; }
             if (!hit && !term) {
                 pslot = (pslot + 2) & t.req_mask;                      // retry on the next pair
-                const uint4* sp = reinterpret_cast<const uint4*>(t.req + pslot);
-                pa0 = ld_nc_v4(sp); pb0 = ld_nc_v4(sp + 1); pa1 = ld_nc_v4(sp + 2); pb1 = ld_nc_v4(sp + 3);
+                const uint4* sp = reinterpret_cast<const uint4*>(pbase + pslot);
+                ld_slot(reinterpret_cast<const ReqSlot*>(sp), peer, pa0, pb0); ld_slot(reinterpret_cast<const ReqSlot*>(sp) + 1, peer, pa1, pb1);
             } else if (!hit) {
                 pend = false; finished = true;
             } else {
@@ -301,9 +303,9 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
             pkey = (iblk == hblk - 1 && staged_cur) ? key : W.kq[iblk & (kKeyRing - 1)][lane];
             pblk = iblk;
             ++iblk;
-            pslot = slot_home(pkey, mdl, t.req_mask);
-            const uint4* sp = reinterpret_cast<const uint4*>(t.req + pslot);
-            pa0 = ld_nc_v4(sp); pb0 = ld_nc_v4(sp + 1); pa1 = ld_nc_v4(sp + 2); pb1 = ld_nc_v4(sp + 3);
+            { const uint64_t hm = home_of(pkey, mdl); pbase = t.req_peer[shard_of(hm, t.shard_bits)]; pslot = hm & t.req_mask & ~1ull; }
+            const uint4* sp = reinterpret_cast<const uint4*>(pbase + pslot);
+            ld_slot(reinterpret_cast<const ReqSlot*>(sp), peer, pa0, pb0); ld_slot(reinterpret_cast<const ReqSlot*>(sp) + 1, peer, pa1, pb1);
             pend = true;
         }
         // 6. retire + refill

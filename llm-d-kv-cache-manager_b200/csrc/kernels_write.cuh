@@ -49,16 +49,14 @@ __device__ __forceinline__ void do_add(const TableView& t, uint32_t model, uint6
                                        const uint16_t* __restrict__ pts, int m) {
     bool created;
     // 1. engineToRequestKeys.Add(engineKey, requestKey)   (in_memory.go:163)
-    const uint64_t ei = eng_lock(t, model, ehash, false, &created);
-    EngSlot* es = t.eng + ei;
+    EngSlot* es = eng_lock(t, model, ehash, false, &created);
     *(volatile uint64_t*)&es->rhash = rhash;
-    if (created) atomicAdd(&t.cnt->eng_full, 1ull);
+    if (created) atomicAdd_system(&cnt_of(t, ehash, model)->eng_full, 1ull);
     eng_unlock(es, make_meta(kStateFull, 0, model));
     // 2. get-or-create the PodCache and add the entries    (in_memory.go:170-203)
-    const uint64_t ri = req_lock(t, model, rhash, false, &created);
-    ReqSlot* rs = t.req + ri;
+    ReqSlot* rs = req_lock(t, model, rhash, false, &created);
     uint32_t count = created ? 0u : meta_count(ld_volatile_u32(&rs->meta));
-    if (created) atomicAdd(&t.cnt->req_full, 1ull);
+    if (created) atomicAdd_system(&cnt_of(t, rhash, model)->req_full, 1ull);
     for (int j = 0; j < m; ++j) count = slot_add_entry(rs, count, pts[j], t.pods_per_key);
     req_unlock(rs, make_meta(kStateFull, count, model));
 }
@@ -66,20 +64,20 @@ __device__ __forceinline__ void do_add(const TableView& t, uint32_t model, uint6
 // Index.Evict (in_memory.go:212-260).
 __device__ __forceinline__ void do_evict(const TableView& t, uint32_t model, uint64_t ehash,
                                          const uint16_t* __restrict__ pts, int m) {
-    uint64_t rhash, ei;
-    if (!eng_find(t, model, ehash, &rhash, &ei)) return;                 // :219-223 silent no-op
+    uint64_t rhash;
+    if (!eng_find(t, model, ehash, &rhash)) return;                      // :219-223 silent no-op
     bool created;
-    const uint64_t ri = req_lock(t, model, rhash, true, &created);
+    ReqSlot* rs = req_lock(t, model, rhash, true, &created);
     bool drop_engine = false;
-    if (ri == ~0ull) {
+    if (!rs) {
         drop_engine = true;                                              // :225-230 stale engine mapping
     } else {
-        ReqSlot* rs = t.req + ri;
         uint32_t count = meta_count(ld_volatile_u32(&rs->meta));
         for (int j = 0; j < m; ++j) count = slot_remove_entry(rs, count, pts[j]);
         if (count == 0) {                                                // :243-256 last entry gone
-            atomicAdd(&t.cnt->req_tomb, 1ull);
-            atomicAdd(&t.cnt->req_full, ~0ull);
+            Counters* c = cnt_of(t, rhash, model);
+            atomicAdd_system(&c->req_tomb, 1ull);
+            atomicAdd_system(&c->req_full, ~0ull);
             req_unlock(rs, make_meta(kStateTomb, 0, model));
             drop_engine = true;
         } else {
@@ -87,11 +85,12 @@ __device__ __forceinline__ void do_evict(const TableView& t, uint32_t model, uin
         }
     }
     if (drop_engine) {
-        const uint64_t e2 = eng_lock(t, model, ehash, true, &created);
-        if (e2 != ~0ull) {
-            atomicAdd(&t.cnt->eng_tomb, 1ull);
-            atomicAdd(&t.cnt->eng_full, ~0ull);
-            eng_unlock(t.eng + e2, make_meta(kStateTomb, 0, model));
+        EngSlot* e2 = eng_lock(t, model, ehash, true, &created);
+        if (e2) {
+            Counters* c = cnt_of(t, ehash, model);
+            atomicAdd_system(&c->eng_tomb, 1ull);
+            atomicAdd_system(&c->eng_full, ~0ull);
+            eng_unlock(e2, make_meta(kStateTomb, 0, model));
         }
     }
 }

@@ -104,6 +104,13 @@ struct kvidx {
 
 namespace {
 
+// a sharded handle is usable once every peer shard has been mapped
+int check_shards(kvidx* x) {
+    for (uint32_t r = 0; r < (1u << x->tv.shard_bits); ++r)
+        if (!x->tv.req_peer[r]) return fail(KVIDX_EINVAL, "shard %u of %u is not connected (kvidx_shard_import / kvidx_shard_attach)", r, 1u << x->tv.shard_bits);
+    return 0;
+}
+
 int refresh_counters(kvidx* x) {
     CK(cudaMemcpyAsync(x->h_cnt, x->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, x->stream));
     CK(cudaStreamSynchronize(x->stream));
@@ -120,6 +127,7 @@ int alloc_tables(kvidx* x, uint64_t req_slots, uint64_t eng_slots, ReqSlot** req
 
 // Drop tombstones by re-inserting live slots into fresh tables.
 int rebuild(kvidx* x) {
+    if (x->tv.shard_bits) return fail(KVIDX_ENOSPC, "sharded table needs compaction (tombstones); not supported while peers map this shard");
     const uint64_t rs = x->tv.req_mask + 1, es = x->tv.eng_mask + 1;
     ReqSlot* nreq; EngSlot* neng;
     int rc = alloc_tables(x, rs, es, &nreq, &neng);
@@ -135,6 +143,7 @@ int rebuild(kvidx* x) {
     CK(cudaStreamSynchronize(x->stream));
     cudaFree(x->tv.req); cudaFree(x->tv.eng);
     x->tv.req = nreq; x->tv.eng = neng;
+    x->tv.req_peer[0] = nreq; x->tv.eng_peer[0] = neng;
     ++x->rebuilds;
     return refresh_counters(x);
 }
@@ -229,6 +238,7 @@ int launch_score(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t 
                  const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
                  int64_t max_blocks = -1) {
     if (n <= 0) return 0;
+    if (int rc = check_shards(x)) return rc;
     if (x->score_kernel == 1) {
         const int T = 128;
         score_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
@@ -466,7 +476,13 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
         CK(cudaEventCreateWithFlags(&x->ev_done[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&x->ev_k[i], cudaEventDisableTiming));
     }
-    uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(4 * c.capacity, 1024));
+    uint32_t shard_bits = 0;
+    if (c.shard_count > 1) {
+        if (c.shard_count > 8 || (c.shard_count & (c.shard_count - 1)) || c.shard_rank >= c.shard_count) { delete x; return fail(KVIDX_EINVAL, "shard_count must be a power of two <= 8 and shard_rank < shard_count"); }
+        while ((1u << shard_bits) < c.shard_count) ++shard_bits;
+    }
+    const uint64_t per_shard = c.shard_count > 1 ? (c.capacity + c.shard_count - 1) / c.shard_count : c.capacity;
+    uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(4 * per_shard, 1024));
     if (slots < 1024) slots = 1024;
     TableView& t = x->tv;
     t.req_mask = slots - 1; t.eng_mask = slots - 1;
@@ -481,6 +497,9 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     CK(cudaMallocHost((void**)&x->h_cnt, sizeof(Counters)));
     memset(x->h_cnt, 0, sizeof(Counters));
     t.cnt = x->d_cnt;
+    t.shard_bits = shard_bits; t.shard_rank = c.shard_count > 1 ? c.shard_rank : 0;
+    for (int i = 0; i < 8; ++i) { t.req_peer[i] = nullptr; t.eng_peer[i] = nullptr; t.cnt_peer[i] = nullptr; }
+    t.req_peer[t.shard_rank] = t.req; t.eng_peer[t.shard_rank] = t.eng; t.cnt_peer[t.shard_rank] = t.cnt;
     CK(cudaStreamSynchronize(x->stream));
     if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
     if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : 0;
@@ -608,6 +627,7 @@ int kvidx_lookup(kvidx_t* x, uint32_t model, const uint64_t* keys, int64_t n, co
     if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
     std::lock_guard<std::mutex> g(x->mu);
     CK(cudaSetDevice(x->device));
+    if (int rc0 = check_shards(x)) return rc0;
     const uint32_t FW = x->tv.filter_words;
     CK(x->d_aux[0].need((size_t)n * 8 + (size_t)FW * 8 + 16));
     CK(x->d_out[0].need((size_t)n * kMaxEnt * 2 + (size_t)n + 16));
@@ -668,6 +688,7 @@ int kvidx_add(kvidx_t* x, uint32_t model, const uint64_t* engine, const uint64_t
     if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
     std::lock_guard<std::mutex> g(x->mu);
     CK(cudaSetDevice(x->device));
+    if (int rc0 = check_shards(x)) return rc0;
     int rc = ensure_room(x, (uint64_t)n);
     if (rc) return rc;
     CK(x->d_misc.need((size_t)n * 16 + (size_t)m * 2 + 16));
@@ -690,6 +711,7 @@ int kvidx_evict(kvidx_t* x, uint32_t model, uint64_t engine, const kvidx_podtier
     if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
     std::lock_guard<std::mutex> g(x->mu);
     CK(cudaSetDevice(x->device));
+    if (int rc0 = check_shards(x)) return rc0;
     CK(x->d_misc.need((size_t)m * 2 + 16));
     CK(cudaMemcpyAsync(x->d_misc.p, pts, (size_t)m * 2, cudaMemcpyHostToDevice, x->stream));
     evict_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, x->d_misc.as<uint16_t>(), m);
@@ -702,6 +724,7 @@ int kvidx_get_request_key(kvidx_t* x, uint32_t model, uint64_t engine, uint64_t*
     if (!x || !out) return fail(KVIDX_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> g(x->mu);
     CK(cudaSetDevice(x->device));
+    if (int rc0 = check_shards(x)) return rc0;
     CK(x->d_misc.need(32));
     uint64_t* d_out = x->d_misc.as<uint64_t>();
     int* d_found = reinterpret_cast<int*>(d_out + 1);
@@ -752,6 +775,7 @@ int kvidx_apply_events(kvidx_t* x, const kvidx_event_t* ev, int64_t n, const uin
     }
     std::lock_guard<std::mutex> g(x->mu);
     CK(cudaSetDevice(x->device));
+    if (int rc0 = check_shards(x)) return rc0;
     int rc = ensure_room(x, new_keys);
     if (rc) return rc;
     // compact non-empty queues
@@ -782,6 +806,54 @@ int kvidx_apply_events(kvidx_t* x, const kvidx_event_t* ev, int64_t n, const uin
     rc = refresh_counters(x);
     if (rc) return rc;
     if (n_dropped_out) *n_dropped_out = (int64_t)(x->h_cnt->dropped_events - dropped_before);
+    return 0;
+}
+
+int kvidx_shard_export(kvidx_t* x, void* out) {
+    if (!x || !out) return fail(KVIDX_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    cudaIpcMemHandle_t h[3];
+    CK(cudaIpcGetMemHandle(&h[0], x->tv.req));
+    CK(cudaIpcGetMemHandle(&h[1], x->tv.eng));
+    CK(cudaIpcGetMemHandle(&h[2], x->d_cnt));
+    static_assert(sizeof(h) == KVIDX_SHARD_HANDLE_BYTES, "handle blob size");
+    memcpy(out, h, sizeof h);
+    return 0;
+}
+
+int kvidx_shard_import(kvidx_t* x, uint32_t rank, const void* handle) {
+    if (!x || !handle) return fail(KVIDX_EINVAL, "bad arguments");
+    if (rank >= (1u << x->tv.shard_bits)) return fail(KVIDX_ERANGE, "rank %u outside shard_count", rank);
+    if (rank == x->tv.shard_rank) return 0;
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    cudaIpcMemHandle_t h[3];
+    memcpy(h, handle, sizeof h);
+    void* p[3] = {nullptr, nullptr, nullptr};
+    for (int i = 0; i < 3; ++i) CK(cudaIpcOpenMemHandle(&p[i], h[i], cudaIpcMemLazyEnablePeerAccess));
+    x->tv.req_peer[rank] = static_cast<ReqSlot*>(p[0]); x->tv.eng_peer[rank] = static_cast<EngSlot*>(p[1]);
+    x->tv.cnt_peer[rank] = static_cast<Counters*>(p[2]);
+    return 0;
+}
+
+int kvidx_shard_attach(kvidx_t* x, uint32_t rank, kvidx_t* other) {
+    if (!x || !other) return fail(KVIDX_EINVAL, "bad arguments");
+    if (rank >= (1u << x->tv.shard_bits)) return fail(KVIDX_ERANGE, "rank %u outside shard_count", rank);
+    if (rank == x->tv.shard_rank) return 0;
+    if (other->tv.req_mask != x->tv.req_mask || other->tv.shard_bits != x->tv.shard_bits || other->tv.shard_rank != rank)
+        return fail(KVIDX_EINVAL, "shard geometry mismatch");
+    std::lock_guard<std::mutex> g(x->mu);
+    CK(cudaSetDevice(x->device));
+    if (other->device != x->device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, x->device, other->device));
+        if (!can) return fail(KVIDX_ECUDA, "device %d cannot access device %d", x->device, other->device);
+        cudaError_t e = cudaDeviceEnablePeerAccess(other->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(KVIDX_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    x->tv.req_peer[rank] = other->tv.req; x->tv.eng_peer[rank] = other->tv.eng; x->tv.cnt_peer[rank] = other->d_cnt;
     return 0;
 }
 

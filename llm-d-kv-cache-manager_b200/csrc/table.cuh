@@ -43,6 +43,9 @@ static_assert(sizeof(EngSlot) == 32, "engine slot is 32 bytes");
 __host__ __device__ __forceinline__ uint64_t slot_home(uint64_t hash, uint32_t model, uint64_t mask) {
     return home_of(hash, model) & mask & ~1ull;
 }
+__host__ __device__ __forceinline__ uint32_t shard_of(uint64_t mixed, uint32_t shard_bits) {
+    return shard_bits ? (uint32_t)(mixed >> (64 - shard_bits)) : 0u;
+}
 __host__ __device__ __forceinline__ uint32_t meta_state(uint32_t m) { return m & kStateMask; }
 __host__ __device__ __forceinline__ uint32_t meta_count(uint32_t m) { return (m >> 4) & 0xfu; }
 __host__ __device__ __forceinline__ uint32_t meta_model(uint32_t m) { return m >> 16; }
@@ -71,6 +74,13 @@ struct TableView {
     uint32_t filter_words;
     Counters* cnt;
     double weight[16];
+    // hash-range sharding over the GPUs of one NVSwitch domain: shard = top bits of the mixed key, slot = low bits.
+    // *_peer[r] is shard r's table mapped into this process (CUDA IPC); entry `shard_rank` is the local one.
+    // Unsharded handles have shard_bits == 0 and *_peer[0] == the local tables.
+    ReqSlot* req_peer[8];
+    EngSlot* eng_peer[8];
+    Counters* cnt_peer[8];
+    uint32_t shard_bits, shard_rank;
 };
 
 #ifdef __CUDACC__
@@ -82,11 +92,19 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) { return 
 
 struct SlotWords { uint4 a, b; };   // a = {tag.lo, tag.hi, ent0|1, ent2|3}; b = {ent4|5, ent6|7, ent8|9, meta}
 
-__device__ __forceinline__ SlotWords load_slot(const ReqSlot* s) {
+// One 32-byte slot as a single 256-bit load (sm_100: LDG.E.256).  Local tables go through the read-only path; a
+// peer GPU's shard is read with a plain (weak) load -- NVLink-mapped memory is not a read-only-cache target.
+__device__ __forceinline__ void ld_slot(const ReqSlot* s, bool peer, uint4& a, uint4& b) {
+    if (peer)
+        asm volatile("ld.global.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(s) : "memory");
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(s));
+}
+__device__ __forceinline__ SlotWords load_slot(const ReqSlot* s, bool peer = false) {
     SlotWords w;
-    const uint4* p = reinterpret_cast<const uint4*>(s);
-    w.a = __ldg(p);
-    w.b = __ldg(p + 1);
+    ld_slot(s, peer, w.a, w.b);
     return w;
 }
 __device__ __forceinline__ uint32_t slot_ent(const SlotWords& w, int j) {
@@ -97,10 +115,12 @@ __device__ __forceinline__ uint32_t slot_ent(const SlotWords& w, int j) {
 
 // Finds the FULL slot holding (model, tag).  Returns false at the first EMPTY slot.
 __device__ __forceinline__ bool req_find(const TableView& t, uint32_t model, uint64_t tag, SlotWords& w, uint64_t* slot_out = nullptr) {
-    uint64_t i = slot_home(tag, model, t.req_mask);
+    const uint64_t hm = home_of(tag, model);
+    const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
+    uint64_t i = hm & t.req_mask & ~1ull;
     const uint32_t tlo = (uint32_t)tag, thi = (uint32_t)(tag >> 32);
     for (;;) {
-        w = load_slot(t.req + i);
+        w = load_slot(base + i, t.shard_bits != 0);
         const uint32_t st = meta_state(w.b.w);
         if (st == kStateEmpty) return false;
         if (st == kStateFull && w.a.x == tlo && w.a.y == thi && meta_model(w.b.w) == model) {
@@ -112,9 +132,11 @@ __device__ __forceinline__ bool req_find(const TableView& t, uint32_t model, uin
 }
 
 __device__ __forceinline__ bool eng_find(const TableView& t, uint32_t model, uint64_t ehash, uint64_t* rhash, uint64_t* slot_out = nullptr) {
-    uint64_t i = slot_home(ehash, model, t.eng_mask);
+    const uint64_t hm = home_of(ehash, model);
+    const EngSlot* base = t.eng_peer[shard_of(hm, t.shard_bits)];
+    uint64_t i = hm & t.eng_mask & ~1ull;
     for (;;) {
-        const EngSlot* s = t.eng + i;
+        const EngSlot* s = base + i;
         const uint32_t m = ld_volatile_u32(&s->meta);
         const uint32_t st = meta_state(m);
         if (st == kStateEmpty) return false;
@@ -133,31 +155,34 @@ __device__ __forceinline__ bool eng_find(const TableView& t, uint32_t model, uin
 // releasing store.  EMPTY -> FULL|LOCK is the claim; tags are written under the lock and are
 // immutable while the slot stays FULL.
 
-// Returns the slot index of (model, tag) with the lock held; *created tells whether the slot
-// was claimed fresh (count 0, tag written).  If must_exist and the key is absent returns ~0.
-__device__ __forceinline__ uint64_t req_lock(const TableView& t, uint32_t model, uint64_t tag, bool must_exist, bool* created) {
-    uint64_t i = slot_home(tag, model, t.req_mask);
+// Returns the slot of (model, tag) with the lock held; *created tells whether the slot was claimed
+// fresh (count 0, tag written).  If must_exist and the key is absent returns nullptr.  The slot may
+// live in a peer GPU's shard: atomics and fences are system scope (NVLink carries both).
+__device__ __forceinline__ ReqSlot* req_lock(const TableView& t, uint32_t model, uint64_t tag, bool must_exist, bool* created) {
+    const uint64_t hm = home_of(tag, model);
+    ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
+    uint64_t i = hm & t.req_mask & ~1ull;
     *created = false;
     for (;;) {
-        ReqSlot* s = t.req + i;
+        ReqSlot* s = base + i;
         const uint32_t m = ld_volatile_u32(&s->meta);
         if (m & kLockBit) continue;                                    // spin on this slot
         const uint32_t st = meta_state(m);
         if (st == kStateEmpty) {
-            if (must_exist) return ~0ull;
+            if (must_exist) return nullptr;
             const uint32_t want = make_meta(kStateFull, 0, model) | kLockBit;
-            if (atomicCAS(&s->meta, m, want) == m) {
+            if (atomicCAS_system(&s->meta, m, want) == m) {
                 *(volatile uint64_t*)&s->tag = tag;
-                __threadfence();
+                __threadfence_system();
                 *created = true;
-                return i;
+                return s;
             }
             continue;                                                  // lost the race: re-examine
         }
         if (st == kStateFull && meta_model(m) == model) {
-            __threadfence();
+            __threadfence_system();
             if (*(const volatile uint64_t*)&s->tag == tag) {
-                if (atomicCAS(&s->meta, m, m | kLockBit) == m) { __threadfence(); return i; }
+                if (atomicCAS_system(&s->meta, m, m | kLockBit) == m) { __threadfence_system(); return s; }
                 continue;
             }
         }
@@ -165,33 +190,35 @@ __device__ __forceinline__ uint64_t req_lock(const TableView& t, uint32_t model,
     }
 }
 __device__ __forceinline__ void req_unlock(ReqSlot* s, uint32_t new_meta) {
-    __threadfence();
+    __threadfence_system();
     *(volatile uint32_t*)&s->meta = new_meta & ~kLockBit;
 }
 
-__device__ __forceinline__ uint64_t eng_lock(const TableView& t, uint32_t model, uint64_t ehash, bool must_exist, bool* created) {
-    uint64_t i = slot_home(ehash, model, t.eng_mask);
+__device__ __forceinline__ EngSlot* eng_lock(const TableView& t, uint32_t model, uint64_t ehash, bool must_exist, bool* created) {
+    const uint64_t hm = home_of(ehash, model);
+    EngSlot* base = t.eng_peer[shard_of(hm, t.shard_bits)];
+    uint64_t i = hm & t.eng_mask & ~1ull;
     *created = false;
     for (;;) {
-        EngSlot* s = t.eng + i;
+        EngSlot* s = base + i;
         const uint32_t m = ld_volatile_u32(&s->meta);
         if (m & kLockBit) continue;
         const uint32_t st = meta_state(m);
         if (st == kStateEmpty) {
-            if (must_exist) return ~0ull;
+            if (must_exist) return nullptr;
             const uint32_t want = make_meta(kStateFull, 0, model) | kLockBit;
-            if (atomicCAS(&s->meta, m, want) == m) {
+            if (atomicCAS_system(&s->meta, m, want) == m) {
                 *(volatile uint64_t*)&s->ehash = ehash;
-                __threadfence();
+                __threadfence_system();
                 *created = true;
-                return i;
+                return s;
             }
             continue;
         }
         if (st == kStateFull && meta_model(m) == model) {
-            __threadfence();
+            __threadfence_system();
             if (*(const volatile uint64_t*)&s->ehash == ehash) {
-                if (atomicCAS(&s->meta, m, m | kLockBit) == m) { __threadfence(); return i; }
+                if (atomicCAS_system(&s->meta, m, m | kLockBit) == m) { __threadfence_system(); return s; }
                 continue;
             }
         }
@@ -199,8 +226,12 @@ __device__ __forceinline__ uint64_t eng_lock(const TableView& t, uint32_t model,
     }
 }
 __device__ __forceinline__ void eng_unlock(EngSlot* s, uint32_t new_meta) {
-    __threadfence();
+    __threadfence_system();
     *(volatile uint32_t*)&s->meta = new_meta & ~kLockBit;
+}
+
+__device__ __forceinline__ Counters* cnt_of(const TableView& t, uint64_t hash, uint32_t model) {
+    return t.cnt_peer[shard_of(home_of(hash, model), t.shard_bits)];
 }
 
 #endif  // __CUDACC__

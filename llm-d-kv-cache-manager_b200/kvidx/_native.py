@@ -26,7 +26,8 @@ class Config(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("device", C.c_int32), ("block_size", C.c_uint32),
                 ("pods_per_key", C.c_uint32), ("init_hash", C.c_uint64), ("capacity", C.c_uint64),
                 ("table_slots", C.c_uint64), ("max_pods", C.c_uint32), ("n_tier_weights", C.c_uint32),
-                ("tier_weight", C.c_double * MAX_TIERS), ("lru_exact", C.c_uint32), ("reserved", C.c_uint32 * 7)]
+                ("tier_weight", C.c_double * MAX_TIERS), ("lru_exact", C.c_uint32), ("shard_rank", C.c_uint32),
+                ("shard_count", C.c_uint32), ("reserved", C.c_uint32 * 5)]
 
 
 class Stats(C.Structure):
@@ -70,6 +71,9 @@ SYMBOLS = {
     "kvidx_hash_keys_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kvidx_apply_events_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kvidx_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
+    "kvidx_shard_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "kvidx_shard_import": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p]),
+    "kvidx_shard_attach": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
 }
 
 _lib = None
@@ -112,7 +116,7 @@ class Index:
     """One libkvidx handle (== kvblock.Index + TokenProcessor + scorer of the reference, ids not strings)."""
 
     def __init__(self, block_size=16, init_hash=None, hash_seed="", capacity=1 << 20, pods_per_key=10,
-                 tier_weights=(1.0, 0.8), max_pods=256, table_slots=0, device=0, lru_exact=0):
+                 tier_weights=(1.0, 0.8), max_pods=256, table_slots=0, device=0, lru_exact=0, shard_rank=0, shard_count=0):
         self.L = load()
         cfg = Config()
         self.L.kvidx_config_default(C.byref(cfg))
@@ -127,6 +131,7 @@ class Index:
         for i, w in enumerate(tier_weights):
             cfg.tier_weight[i] = float(w)
         cfg.lru_exact = lru_exact
+        cfg.shard_rank, cfg.shard_count = shard_rank, shard_count
         h = C.c_void_p()
         rc = self.L.kvidx_create(C.byref(cfg), C.byref(h))
         if rc:
@@ -167,6 +172,20 @@ class Index:
         s = Stats()
         self._ck(self.L.kvidx_get_stats(self.h, C.byref(s)))
         return {n: getattr(s, n) for n, _ in Stats._fields_}
+
+    # -- hash-range sharding (one handle per GPU) --
+    SHARD_HANDLE_BYTES = 192
+
+    def shard_export(self) -> bytes:
+        buf = C.create_string_buffer(self.SHARD_HANDLE_BYTES)
+        self._ck(self.L.kvidx_shard_export(self.h, buf))
+        return buf.raw
+
+    def shard_import(self, rank: int, handle: bytes):
+        self._ck(self.L.kvidx_shard_import(self.h, rank, handle))
+
+    def shard_attach(self, rank: int, other: "Index"):
+        self._ck(self.L.kvidx_shard_attach(self.h, rank, other.h))
 
     # -- read path --
     def hash_keys(self, tok, tok_off, parent=None, parent_valid=None):

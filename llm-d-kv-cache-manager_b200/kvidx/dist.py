@@ -77,3 +77,26 @@ def gather_scores(local_scores: np.ndarray, n_total: int, device=None):
         lo, hi = shard_range(n_total, r, world)
         out[lo:hi] = parts[r].cpu().numpy()[: hi - lo]
     return out
+
+
+def connect_shards(ix, device=None):
+    """Hash-range sharded mode: exchange the CUDA-IPC handle blobs of every rank's shard (one all_gather of 192 bytes
+    per rank -- the only collective this mode needs) and map them.  After this call every kernel of `ix` can probe /
+    lock slots of any shard through NVLink peer memory."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.frombuffer(bytearray(ix.shard_export()), dtype=torch.uint8)
+    if device is not None:
+        mine = mine.to(device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    for r in range(world):
+        if r != rank:
+            ix.shard_import(r, bytes(parts[r].cpu().numpy().tobytes()))
+    dist.barrier()
+
+
+def events_for_rank(events, rank: int, world: int):
+    """Ingest rule of the sharded mode: all events of one pod go through one rank (pod id modulo world), which keeps
+    the reference's per-pod ordering (kvevents/pool.go:129-144) without any cross-GPU coordination."""
+    pods = events["podtier"] >> 4
+    return events[(pods % world) == rank]
