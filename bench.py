@@ -230,7 +230,7 @@ def run_reference(args):
                             "p99_latency_ms": float(np.percentile(lat, 99)) / 1e6, "p50_latency_ms": float(np.percentile(lat, 50)) / 1e6},
            "e2e": {"value": value, "unit": "prompts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -257,18 +257,37 @@ def run_ours(args):
     Q = int(os.environ.get("KVIDX_BENCH_BATCH", str(524288)))      # prompts resident in HBM per step (per GPU)
     QE = int(os.environ.get("KVIDX_BENCH_E2E_BATCH", str(65536)))  # prompts per e2e step (host buffers)
 
-    # ---- index: filled through the write path (BlockStored events), every rank holds a full replica ----
-    ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + 1024, max_pods=wl.P, tier_weights=WEIGHTS, device=local)
+    # ---- index: filled through the write path (BlockStored events) ----
+    #   replicas (default): every rank holds the full index, prompts are sharded, no data-path collective
+    #   sharded (KVIDX_BENCH_MODE=sharded): the tables are hash-range sharded over the ranks; every rank maps its peers'
+    #     shards (CUDA IPC, one 192-byte all_gather) and probes them through NVLink peer memory from the same kernels;
+    #     each rank ingests the events of its own pods (pod % world == rank)
+    from kvidx import dist as kd
+    mode = os.environ.get("KVIDX_BENCH_MODE", "replicas") if world > 1 else "single"
+    if mode == "sharded":
+        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + 1024 * world, max_pods=wl.P, tier_weights=WEIGHTS, device=local,
+                         shard_rank=rank, shard_count=world)
+        kd.connect_shards(ix, dev)
+    else:
+        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + 1024, max_pods=wl.P, tier_weights=WEIGHTS, device=local)
     t0 = time.time()
     n_ev = 0
     for d0 in range(0, wl.D, 4096):
         ev, hs, tk = wl.fill_events(d0, min(wl.D, d0 + 4096))
+        if mode == "sharded":
+            ev = kd.events_for_rank(ev, rank, world)
         rc, dropped = ix.apply_events(ev, hs, tk)
         assert rc == 0 and dropped == 0, (rc, dropped, ix.last_error())
         n_ev += len(ev)
+    barrier()
     fill_s = time.time() - t0
     st = ix.stats()
-    assert st["request_keys"] == wl.n_blocks, st
+    if mode == "sharded":
+        tot = torch.tensor([st["request_keys"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot)
+        assert int(tot.item()) == wl.n_blocks, (int(tot.item()), wl.n_blocks)
+    else:
+        assert st["request_keys"] == wl.n_blocks, st
     log("[fill] %d BlockStored events -> %d request keys in %.1fs (host event generation included)" % (n_ev, st["request_keys"], fill_s))
 
     # ---- device-resident batch (rank r scores its own slice of the query stream) ----
@@ -412,16 +431,38 @@ def run_ours(args):
                           "batch_prompts_per_gpu": Q, "query_mix": "m uniform in [0,n] matched blocks + random tail",
                           "queries_per_document": Q / wl.D,
                           "l2_policy": "inputs (%.1f GB tokens + %.1f GB table) larger than the 126 MB L2; no flush" % (Q * wl.T * 4 / 1e9, st["request_slots"] * 32 / 1e9),
-                          "multi_gpu": "replicas: full index per GPU, prompts sharded, no data-path collective" if world > 1 else "single GPU",
+                          "multi_gpu": {"single": "single GPU", "replicas": "replicas: full index per GPU, prompts sharded, no data-path collective",
+                                        "sharded": "hash-range sharded tables, probes over NVLink peer memory (CUDA IPC), per-pod ingest ranks"}[mode],
                           "index_fill_s": fill_s, "fill_events": n_ev},
                "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k,
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Rank 0 must print exactly ONE JSON line on stdout; NCCL / torchrun helpers write banners with C-level
+    printf.  Point fd 1 at stderr for the duration of the run and restore it for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
