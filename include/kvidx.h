@@ -79,9 +79,13 @@ typedef struct kvidx_config {
     uint32_t n_tier_weights;   /* entries of tier_weight[] that are configured                  */
     double   tier_weight[KVIDX_MAX_TIERS]; /* weight of tier id i; ids >= n_tier_weights score 1.0
                                               (unknown tier => 1.0, kvblock_scorer.go:93-98)    */
-    uint32_t lru_exact;        /* 1: track key recency so that Size-cap eviction is exact LRU
-                                  (in_memory.go:59,118,170); 0: recency not tracked, inserting
-                                  beyond `capacity` fails with KVIDX_ENOSPC                      */
+    uint32_t lru_exact;        /* 1: track key recency (a stamp per slot, written by Lookup / Score / Add / Evict /
+                                  GetRequestKey exactly where golang-lru refreshes) and evict the least recently used
+                                  request / engine keys when a write call leaves more than `capacity` of them
+                                  (in_memory.go:59,64,118,163,170).  Exact at call granularity.  Score() then probes
+                                  every key of a prompt (the reference's Lookup has no early exit), so it is the slow,
+                                  semantics-first mode.  0 (default): recency is not tracked and `capacity` only sizes
+                                  the table -- right whenever the fleet's block count stays below Size (default 1e8). */
     uint32_t shard_rank;       /* hash-range sharding over the GPUs of one NVSwitch domain: this handle */
     uint32_t shard_count;      /* owns shard `shard_rank` of `shard_count` (power of two <= 8; 0 or 1 = unsharded).   */
                                /* `capacity` stays the TOTAL key budget; each shard holds capacity/shard_count.        */

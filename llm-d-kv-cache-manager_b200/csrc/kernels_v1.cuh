@@ -48,13 +48,15 @@ __device__ __forceinline__ const uint64_t* filter_row(const uint64_t* __restrict
 // in_memory.go:119-122 cannot trigger; it is still honoured via cut_out for completeness.)
 __global__ void lookup_kernel_v1(TableView t, uint32_t model, const uint64_t* __restrict__ keys, int64_t n,
                                  const uint64_t* __restrict__ filter, uint16_t* __restrict__ podtier_out,
-                                 uint8_t* __restrict__ cnt_out, int* __restrict__ cut_out) {
+                                 uint8_t* __restrict__ cnt_out, int* __restrict__ cut_out, unsigned long long stamp_base) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t* frow = filter_row(filter, 0, t.filter_words);
     SlotWords w;
     uint32_t c = 0;
-    if (req_find(t, model, keys[i], w)) {
+    uint64_t slot = 0;
+    if (req_find(t, model, keys[i], w, &slot)) {
+        if (t.req_stamp) t.req_stamp[slot] = stamp_base + (unsigned long long)i;      // data.Get refreshes recency (in_memory.go:118)
         const uint32_t cnt = meta_count(w.b.w);
         if (cnt == 0) atomicMin(cut_out, (int)min(i, (int64_t)0x7fffffff));
         for (uint32_t j = 0; j < cnt; ++j) {
@@ -109,7 +111,7 @@ __global__ void score_kernel_v1(TableView t, const uint32_t* __restrict__ tok, c
                                 int64_t tok_base, int64_t n_prompts, const uint32_t* __restrict__ model, uint32_t model0,
                                 const uint64_t* __restrict__ filter, double* __restrict__ dense_out,
                                 uint16_t* __restrict__ sp_pods, double* __restrict__ sp_scores, uint8_t* __restrict__ sp_cnt,
-                                uint8_t* __restrict__ has_keys) {
+                                uint8_t* __restrict__ has_keys, unsigned long long stamp_base = 0, unsigned long long stamp_stride = 0) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_prompts) return;
     const int64_t b = tok_off[i] - tok_base, e = tok_off[i + 1] - tok_base;
@@ -118,13 +120,20 @@ __global__ void score_kernel_v1(TableView t, const uint32_t* __restrict__ tok, c
     const uint64_t* frow = filter_row(filter, i, t.filter_words);
     ScoreState s; s.k = 0; s.alive = 0;
     uint64_t h = t.init_hash;
+    bool walking = true;
     for (int64_t k = 0; k < nblk; ++k) {
         h = hash_block_global(h, tok + b + k * t.block_size, t.block_size);
         SlotWords w;
-        const bool hit = req_find(t, mdl, h, w);
-        if (k == 0) { if (!hit) break; s.first(t, w, frow); }
-        else { if (!hit) break; s.next(t, w); }
-        if (!s.alive) break;
+        uint64_t slot = 0;
+        const bool hit = req_find(t, mdl, h, w, &slot);
+        // exact-LRU mode: the reference's Lookup touches EVERY key of the prompt that is present, also past the end of
+        // the consecutive prefix (in_memory.go:117-139), so the probe loop runs to the last block and stamps them.
+        if (hit && t.req_stamp) t.req_stamp[slot] = stamp_base + (unsigned long long)i * stamp_stride + (unsigned long long)k;
+        if (walking) {
+            if (!hit) walking = false;
+            else { if (k == 0) s.first(t, w, frow); else s.next(t, w); if (!s.alive) walking = false; }
+        }
+        if (!walking && !t.req_stamp) break;
     }
     if (has_keys) has_keys[i] = nblk > 0;
     if (dense_out) {

@@ -88,6 +88,8 @@ struct kvidx {
     Counters* d_cnt = nullptr;
     Counters* h_cnt = nullptr;     // pinned mirror
     uint64_t rebuilds = 0, launches = 0;
+    int64_t last_batch_events = 1 << 20;   // events in the batch being applied (sizes the stamp range)
+    unsigned long long clock = 1;   // exact-LRU mode: recency stamps handed to kernels (calls on a handle are serialised)
     std::mutex mu;
     // scratch (guarded by mu)
     DevBuf d_tok[2], d_off[2], d_model[2], d_filter[2], d_out[2], d_aux[2], d_misc, d_ev, d_hash, d_evtok, d_qoff;
@@ -111,6 +113,8 @@ int check_shards(kvidx* x) {
     return 0;
 }
 
+unsigned long long reserve_stamps(kvidx* x, unsigned long long n) { const unsigned long long b = x->clock; x->clock += n + 1; return b; }
+
 int refresh_counters(kvidx* x) {
     CK(cudaMemcpyAsync(x->h_cnt, x->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, x->stream));
     CK(cudaStreamSynchronize(x->stream));
@@ -133,7 +137,9 @@ int rebuild(kvidx* x) {
     int rc = alloc_tables(x, rs, es, &nreq, &neng);
     if (rc) return rc;
     const int T = 256;
-    rebuild_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, rs, nreq, rs - 1);
+    unsigned long long* nstamp = nullptr;
+    if (x->tv.req_stamp) { CK(cudaMalloc((void**)&nstamp, rs * 8)); CK(cudaMemsetAsync(nstamp, 0, rs * 8, x->stream)); }
+    rebuild_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, rs, nreq, rs - 1, x->tv.req_stamp, nstamp);
     rebuild_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, x->stream>>>(x->tv.eng, es, neng, es - 1);
     x->launches += 2;
     CK(cudaGetLastError());
@@ -142,6 +148,7 @@ int rebuild(kvidx* x) {
     CK(cudaMemsetAsync(&x->d_cnt->eng_tomb, 0, sizeof(unsigned long long), x->stream));
     CK(cudaStreamSynchronize(x->stream));
     cudaFree(x->tv.req); cudaFree(x->tv.eng);
+    if (x->tv.req_stamp) { cudaFree(x->tv.req_stamp); x->tv.req_stamp = nstamp; }
     x->tv.req = nreq; x->tv.eng = neng;
     x->tv.req_peer[0] = nreq; x->tv.eng_peer[0] = neng;
     ++x->rebuilds;
@@ -159,6 +166,35 @@ int ensure_room(kvidx* x, uint64_t incoming) {
         if ((d.req_full + incoming) * 10 > rs * 9 || (d.eng_full + incoming) * 10 > es * 9)
             return fail(KVIDX_ENOSPC, "table full: %llu request keys + %llu incoming in %llu slots",
                         (unsigned long long)d.req_full, (unsigned long long)incoming, (unsigned long long)rs);
+    }
+    return 0;
+}
+
+// exact-LRU mode: after a write call, evict least-recently-used keys until both maps respect InMemoryIndexConfig.Size
+// (lru.Cache evicts the back of its list when Len() > size; in_memory.go:59,64).  Exact at call granularity.
+int enforce_caps(kvidx* x) {
+    if (!x->tv.req_stamp) return 0;
+    int rc = refresh_counters(x);
+    if (rc) return rc;
+    CK(x->d_misc.need(64));
+    unsigned long long* d_v = x->d_misc.as<unsigned long long>();
+    const uint64_t rs = x->tv.req_mask + 1, es = x->tv.eng_mask + 1;
+    const int T = 256;
+    while (x->h_cnt->req_full > x->tv.capacity) {
+        CK(cudaMemsetAsync(d_v, 0xff, 8, x->stream));
+        lru_min_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, x->tv.req_stamp, rs, d_v);
+        lru_drop_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, x->tv.req_stamp, rs, d_v, x->d_cnt);
+        x->launches += 2;
+        CK(cudaGetLastError());
+        if ((rc = refresh_counters(x))) return rc;
+    }
+    while (x->h_cnt->eng_full > x->tv.capacity) {
+        CK(cudaMemsetAsync(d_v, 0xff, 8, x->stream));
+        lru_min_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, x->stream>>>(x->tv.eng, es, d_v);
+        lru_drop_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, x->stream>>>(x->tv.eng, es, d_v, x->d_cnt);
+        x->launches += 2;
+        CK(cudaGetLastError());
+        if ((rc = refresh_counters(x))) return rc;
     }
     return 0;
 }
@@ -239,10 +275,13 @@ int launch_score(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t 
                  int64_t max_blocks = -1) {
     if (n <= 0) return 0;
     if (int rc = check_shards(x)) return rc;
-    if (x->score_kernel == 1) {
+    if (x->score_kernel == 1 || x->tv.req_stamp) {
+        // exact-LRU mode always takes this kernel: Lookup must touch every present key of a prompt (no early exit)
         const int T = 128;
+        const unsigned long long stride = 1ull << 20;
+        const unsigned long long sb = x->tv.req_stamp ? reserve_stamps(x, (unsigned long long)n * stride) : 0;
         score_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
-                                                                  o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys);
+                                                                  o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, sb, stride);
         x->launches += 1;
     } else if (x->tv.block_size == 16 && n < (1ll << 32) && (x->score_path == 2 || (x->score_path == 0 && n >= x->rounds_min))) {
         return launch_score_rounds(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks);
@@ -492,6 +531,11 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     t.req_stamp = nullptr;
     int rc = alloc_tables(x, slots, slots, &t.req, &t.eng);
     if (rc) { delete x; return rc; }
+    if (c.lru_exact) {
+        if (c.shard_count > 1) { delete x; return fail(KVIDX_EINVAL, "lru_exact is not supported on a sharded index"); }
+        CK(cudaMalloc((void**)&t.req_stamp, slots * 8));
+        CK(cudaMemsetAsync(t.req_stamp, 0, slots * 8, x->stream));
+    }
     CK(cudaMalloc((void**)&x->d_cnt, sizeof(Counters)));
     CK(cudaMemsetAsync(x->d_cnt, 0, sizeof(Counters), x->stream));
     CK(cudaMallocHost((void**)&x->h_cnt, sizeof(Counters)));
@@ -645,7 +689,8 @@ int kvidx_lookup(kvidx_t* x, uint32_t model, const uint64_t* keys, int64_t n, co
     uint16_t* d_pt = x->d_out[0].as<uint16_t>();
     uint8_t* d_cnt = x->d_out[0].as<uint8_t>() + (size_t)n * kMaxEnt * 2;
     const int T = 128;
-    lookup_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, model, d_keys, n, d_f, d_pt, d_cnt, d_cut);
+    lookup_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, model, d_keys, n, d_f, d_pt, d_cnt, d_cut,
+                                                                      reserve_stamps(x, (unsigned long long)n));
     x->launches += 1;
     CK(cudaGetLastError());
     int cut = big;
@@ -699,10 +744,13 @@ int kvidx_add(kvidx_t* x, uint32_t model, const uint64_t* engine, const uint64_t
     const int T = 128;
     add_kernel<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, model, reinterpret_cast<uint64_t*>(d),
                                                                 reinterpret_cast<uint64_t*>(d + (size_t)n * 8), n,
-                                                                reinterpret_cast<uint16_t*>(d + (size_t)n * 16), m);
+                                                                reinterpret_cast<uint16_t*>(d + (size_t)n * 16), m,
+                                                                reserve_stamps(x, 2ull * (unsigned long long)n + 2));
     x->launches += 1;
     CK(cudaGetLastError());
-    return refresh_counters(x);
+    rc = refresh_counters(x);
+    if (rc) return rc;
+    return enforce_caps(x);
 }
 
 int kvidx_evict(kvidx_t* x, uint32_t model, uint64_t engine, const kvidx_podtier_t* pts, int32_t m) {
@@ -714,7 +762,7 @@ int kvidx_evict(kvidx_t* x, uint32_t model, uint64_t engine, const kvidx_podtier
     if (int rc0 = check_shards(x)) return rc0;
     CK(x->d_misc.need((size_t)m * 2 + 16));
     CK(cudaMemcpyAsync(x->d_misc.p, pts, (size_t)m * 2, cudaMemcpyHostToDevice, x->stream));
-    evict_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, x->d_misc.as<uint16_t>(), m);
+    evict_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, x->d_misc.as<uint16_t>(), m, reserve_stamps(x, 4));
     x->launches += 1;
     CK(cudaGetLastError());
     return refresh_counters(x);
@@ -728,7 +776,7 @@ int kvidx_get_request_key(kvidx_t* x, uint32_t model, uint64_t engine, uint64_t*
     CK(x->d_misc.need(32));
     uint64_t* d_out = x->d_misc.as<uint64_t>();
     int* d_found = reinterpret_cast<int*>(d_out + 1);
-    get_request_key_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, d_out, d_found);
+    get_request_key_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, d_out, d_found, x->tv.req_stamp ? reserve_stamps(x, 1) : 0);
     x->launches += 1;
     CK(cudaGetLastError());
     struct { uint64_t r; int f; int pad; } h{};
@@ -747,7 +795,8 @@ int kvidx_apply_events_dev(kvidx_t* x, const kvidx_event_t* d_ev_sorted, const i
     CK(cudaSetDevice(x->device));
     const int T = 128;   // 4 queues per CTA
     const int64_t warps = n_queues;
-    apply_events_kernel<<<(unsigned)((warps * 32 + T - 1) / T), T, 0, x->stream>>>(x->tv, d_ev_sorted, d_queue_off, n_queues, d_hashes, d_tokens);
+    apply_events_kernel<<<(unsigned)((warps * 32 + T - 1) / T), T, 0, x->stream>>>(x->tv, d_ev_sorted, d_queue_off, n_queues, d_hashes, d_tokens,
+                                                                                    x->tv.req_stamp ? reserve_stamps(x, (1ull << 20) * (unsigned long long)x->last_batch_events) : 0);
     x->launches += 1;
     CK(cudaGetLastError());
     return 0;
@@ -800,13 +849,14 @@ int kvidx_apply_events(kvidx_t* x, const kvidx_event_t* ev, int64_t n, const uin
     if (n_hashes > 0) CK(cudaMemcpyAsync(x->d_hash.p, hashes, (size_t)n_hashes * 8, cudaMemcpyHostToDevice, x->stream));
     if (n_tokens > 0) CK(cudaMemcpyAsync(x->d_evtok.p, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, x->stream));
     const unsigned long long dropped_before = x->h_cnt->dropped_events;
+    x->last_batch_events = n;
     rc = kvidx_apply_events_dev(x, x->d_ev.as<kvidx_event_t>(), x->d_qoff.as<int64_t>(), nq, x->d_hash.as<uint64_t>(),
                                 x->d_evtok.as<uint32_t>(), nullptr);
     if (rc) return rc;
     rc = refresh_counters(x);
     if (rc) return rc;
     if (n_dropped_out) *n_dropped_out = (int64_t)(x->h_cnt->dropped_events - dropped_before);
-    return 0;
+    return enforce_caps(x);
 }
 
 int kvidx_shard_export(kvidx_t* x, void* out) {

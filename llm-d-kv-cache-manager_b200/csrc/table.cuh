@@ -64,7 +64,8 @@ struct Counters {
 struct TableView {
     ReqSlot* req;
     EngSlot* eng;
-    uint32_t* req_stamp;       // per-request-slot recency stamp, exact-LRU mode only (else nullptr)
+    unsigned long long* req_stamp;   // per-request-slot recency stamp: exact-LRU mode only (else nullptr).  Engine
+                                     // slots carry their stamp inline.  Larger = more recent (golang-lru front).
     uint64_t req_mask, eng_mask;
     uint64_t capacity;
     uint64_t init_hash;
@@ -131,7 +132,8 @@ __device__ __forceinline__ bool req_find(const TableView& t, uint32_t model, uin
     }
 }
 
-__device__ __forceinline__ bool eng_find(const TableView& t, uint32_t model, uint64_t ehash, uint64_t* rhash, uint64_t* slot_out = nullptr) {
+__device__ __forceinline__ bool eng_find(const TableView& t, uint32_t model, uint64_t ehash, uint64_t* rhash, uint64_t* slot_out = nullptr,
+                                         unsigned long long stamp = 0) {
     const uint64_t hm = home_of(ehash, model);
     const EngSlot* base = t.eng_peer[shard_of(hm, t.shard_bits)];
     uint64_t i = hm & t.eng_mask & ~1ull;
@@ -143,6 +145,7 @@ __device__ __forceinline__ bool eng_find(const TableView& t, uint32_t model, uin
         if (st == kStateFull && !(m & kLockBit) && meta_model(m) == model && *(const volatile uint64_t*)&s->ehash == ehash) {
             *rhash = *(const volatile uint64_t*)&s->rhash;
             if (slot_out) *slot_out = i;
+            if (stamp && t.req_stamp) *(volatile uint64_t*)&const_cast<EngSlot*>(s)->stamp = stamp;   // lru Get refreshes recency
             return true;
         }
         if (st == kStateFull && (m & kLockBit)) continue;   // being written: re-read this slot

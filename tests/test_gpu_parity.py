@@ -359,3 +359,63 @@ def test_rebuild_after_tombstones():
     assert rc == 0 and (cnt == 1).all() and (pt[:, 0] == PT(1)).all()
     for e, r in list(live.items())[:50]:
         assert ix.get_request_key(0, e) == (0, r)
+
+
+# ---- exact key-LRU mode (InMemoryIndexConfig.Size) --------------------------------------------------------------
+def test_index_size_cap_exact_lru():
+    """pkg/kvcache/kvblock/in_memory_test.go:44-83: Size=2, the third Add evicts the first key; the lookup still returns
+    the other two (a missing first key does not cut)."""
+    ix = kvidx.Index(capacity=2, pods_per_key=1, lru_exact=1)
+    assert ix.add(0, [72735753], [79215516], [PT(1)]) == 0
+    assert ix.add(0, [41341092], [12871930], [PT(2)]) == 0
+    assert ix.add(0, [34012886], [69914638], [PT(3, 1)]) == 0
+    rc, pt, cnt = ix.lookup(0, [79215516, 12871930, 69914638])
+    assert rc == 0 and cnt.tolist() == [0, 1, 1] and pt[1, 0] == PT(2) and pt[2, 0] == PT(3, 1)
+    assert ix.stats()["request_keys"] == 2 and ix.stats()["engine_keys"] == 2
+    # Lookup refreshes recency (in_memory.go:118): touch key2, add a fourth key -> key3 is now the oldest and goes
+    assert ix.lookup(0, [12871930])[0] == 0
+    assert ix.add(0, [555], [777], [PT(4)]) == 0
+    rc, pt, cnt = ix.lookup(0, [12871930, 69914638, 777])
+    assert cnt.tolist() == [1, 0, 1]
+
+
+def test_exact_lru_random_stream_vs_oracle():
+    """Size-capped index under a random single-block event stream with lookups and Score() calls in between (both refresh
+    recency in the reference).  One call = one oracle operation, so call-granular exactness is full exactness here."""
+    rng = np.random.default_rng(41)
+    BS, P, CAP = 16, 12, 40
+    ix = kvidx.Index(block_size=BS, capacity=CAP, pods_per_key=3, max_pods=16, lru_exact=1)
+    co = COracle(block_size=BS, size=CAP, pod_cache_size=3, max_pods=16)
+    docs = [rng.integers(0, 128256, size=BS * int(rng.integers(2, 9))).tolist() for _ in range(14)]
+    for step in range(700):
+        pod = int(rng.integers(0, P)); tier = int(rng.integers(0, 2))
+        d = int(rng.integers(0, len(docs))); nb = len(docs[d]) // BS
+        b = int(rng.integers(0, nb))
+        r = np.zeros(1, EVENT_DTYPE)
+        r["podtier"] = (pod << 4) | tier
+        if rng.random() < 0.7:
+            r["op"] = 0; r["has_parent"] = b > 0; r["parent_hash"] = d * 1000 + b - 1 if b > 0 else 0
+            r["n_hashes"] = 1; r["n_tokens"] = BS
+            hs = np.array([d * 1000 + b], np.uint64); tk = np.array(docs[d][b * BS:(b + 1) * BS], np.uint32)
+        else:
+            r["op"] = 1; r["n_hashes"] = 1
+            hs = np.array([d * 1000 + b], np.uint64); tk = np.zeros(0, np.uint32)
+        assert ix.apply_events(r, hs, tk)[0] == 0 and co.apply_events(r, hs, tk)[0] == 0
+        if step % 5 == 4:
+            q = docs[int(rng.integers(0, len(docs)))]
+            q = q[:BS * int(rng.integers(0, len(q) // BS + 1))] + rng.integers(0, 128256, size=int(rng.integers(0, 20))).tolist()
+            tok, off = csr([q])
+            s1, h1 = ix.score_batch(tok, off)
+            s2, h2, _, _ = co.score_batch(tok, off)
+            assert np.array_equal(s1, s2) and np.array_equal(h1, h2), step
+        if step % 7 == 6:
+            d2 = docs[int(rng.integers(0, len(docs)))]
+            keys, _ = co.hash_keys(np.array(d2, np.uint32), [0, len(d2)])
+            uk = np.unique(keys)
+            r1 = ix.lookup(0, uk); r2 = co.lookup(0, uk)
+            assert np.array_equal(r1[2], r2[2]), step
+            for i in range(len(uk)):
+                assert np.array_equal(r1[1][i, :r1[2][i]], r2[1][i, :r2[2][i]])
+        st = ix.stats()
+        assert st["request_keys"] == co.len_request() and st["engine_keys"] == co.len_engine(), step
+    assert ix.stats()["request_keys"] <= CAP
