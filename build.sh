@@ -5,4 +5,4 @@ cd "$(dirname "$0")"
 OUT=${KVIDX_OUT:-llm-d-kv-cache-manager_b200/lib}
 mkdir -p $OUT
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall -shared \
-     -Xptxas -v "$@" -o $OUT/libkvidx.so llm-d-kv-cache-manager_b200/csrc/kvidx.cu 2>&1
+     -Xptxas -v "$@" -o $OUT/libkvidx.so llm-d-kv-cache-manager_b200/csrc/kvidx.cu llm-d-kv-cache-manager_b200/host/kvhost.cpp 2>&1

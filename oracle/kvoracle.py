@@ -379,40 +379,216 @@ def get_hash_as_uint64(h) -> int:
     raise TypeError("unsupported hash type: %r" % type(h))
 
 
-def decode_event_batch(payload: bytes) -> list:
-    """processEvent's msgpack decoding (kvevents/pool.go:177-244, events.go:38-96).
+class TInt(int):
+    """An integer together with the msgpack type code it arrived with.  vmihailenco/msgpack's DecodeInterface returns
+    int8..int64 / uint8..uint64 according to the wire code, and getHashAsUint64 (kvevents/pool.go:343-367) only accepts
+    the uint64 (0xcf) and int64 (0xd3) forms -- so the width matters for parity."""
+    code = 0
 
-    EventBatch = [ts, [event...], dp_rank?]; each event is an array-tagged
-    union [tag, fields...]; trailing omitempty fields may be absent.  Malformed
-    events are skipped, a malformed batch yields [] (poison pill dropped).
-    """
-    import msgpack
+    def __new__(cls, v, code):
+        o = super().__new__(cls, v)
+        o.code = code
+        return o
+
+
+class _MpError(Exception):
+    pass
+
+
+def _mp_read(buf: bytes, pos: int, depth: int = 0):
+    """Minimal msgpack reader: returns (value, new_pos).  ints -> TInt, str/bin -> ("str"|"bin", bytes) tuples are NOT
+    used; str -> str (bytes if not UTF-8), bin -> bytes, arrays -> list, maps -> dict, ext -> ("ext", bytes)."""
+    if depth > 64 or pos >= len(buf):
+        raise _MpError("truncated")
+    b = buf[pos]; pos += 1
+
+    def take(n):
+        nonlocal pos
+        if pos + n > len(buf):
+            raise _MpError("truncated")
+        v = buf[pos:pos + n]; pos += n
+        return v
+
+    if b <= 0x7F:
+        return TInt(b, b), pos
+    if b >= 0xE0:
+        return TInt(b - 256, b), pos
+    if 0xA0 <= b <= 0xBF:
+        return _mp_str(take(b & 0x1F)), pos
+    if 0x90 <= b <= 0x9F or b in (0xDC, 0xDD):
+        n = b & 0x0F if b <= 0x9F else int.from_bytes(take(2 if b == 0xDC else 4), "big")
+        out = []
+        for _ in range(n):
+            v, pos = _mp_read(buf, pos, depth + 1)
+            out.append(v)
+        return out, pos
+    if 0x80 <= b <= 0x8F or b in (0xDE, 0xDF):
+        n = b & 0x0F if b <= 0x8F else int.from_bytes(take(2 if b == 0xDE else 4), "big")
+        out = {}
+        for _ in range(n):
+            k, pos = _mp_read(buf, pos, depth + 1)
+            v, pos = _mp_read(buf, pos, depth + 1)
+            out[repr(k)] = v
+        return out, pos
+    if b == 0xC0:
+        return None, pos
+    if b in (0xC2, 0xC3):
+        return b == 0xC3, pos
+    if b in (0xC4, 0xC5, 0xC6):
+        n = int.from_bytes(take(1 << (b - 0xC4)), "big")
+        return bytes(take(n)), pos
+    if b in (0xC7, 0xC8, 0xC9):
+        n = int.from_bytes(take(1 << (b - 0xC7)), "big"); take(1)
+        return ("ext", bytes(take(n))), pos
+    if b == 0xCA:
+        import struct
+        return struct.unpack(">f", take(4))[0], pos
+    if b == 0xCB:
+        import struct
+        return struct.unpack(">d", take(8))[0], pos
+    if 0xCC <= b <= 0xCF:
+        return TInt(int.from_bytes(take(1 << (b - 0xCC)), "big"), b), pos
+    if 0xD0 <= b <= 0xD3:
+        return TInt(int.from_bytes(take(1 << (b - 0xD0)), "big", signed=True), b), pos
+    if 0xD4 <= b <= 0xD8:
+        take(1)
+        return ("ext", bytes(take(1 << (b - 0xD4)))), pos
+    if b in (0xD9, 0xDA, 0xDB):
+        n = int.from_bytes(take(1 << (b - 0xD9)), "big")
+        return _mp_str(take(n)), pos
+    raise _MpError("invalid code 0x%02x" % b)
+
+
+class _MpStr(str):
+    """str that remembers its raw bytes (Go strings are byte strings; lower() must not choke on invalid UTF-8)."""
+    raw = b""
+
+
+def _mp_str(raw: bytes):
+    o = _MpStr(raw.decode("utf-8", "surrogateescape"))
+    o.raw = bytes(raw)
+    return o
+
+
+def typed_hash(v):
+    """getHashAsUint64 on a DecodeInterface-typed value: only uint64 / int64 coded ints and byte slices pass."""
+    if isinstance(v, TInt):
+        if v.code in (0xCF, 0xD3):
+            return int(v) & MASK64
+        raise TypeError("unsupported hash type: int code 0x%02x" % v.code)
+    if isinstance(v, (bytes, bytearray)) and not isinstance(v, str):
+        return get_hash_as_uint64(bytes(v))
+    raise TypeError("unsupported hash type: %r" % type(v))
+
+
+def _is_int(v):
+    return isinstance(v, TInt)
+
+
+def decode_event_batch(payload: bytes) -> list:
+    """processEvent's msgpack decoding (kvevents/pool.go:177-244, events.go:38-96) with vmihailenco/msgpack v5 typing.
+
+    EventBatch = [ts, [event...], dp_rank?] decoded all-or-nothing (any error drops the message, pool.go:182-187);
+    each event is an array-tagged union [tag, fields...]; array-encoded structs take fields positionally, missing
+    trailing fields stay zero, extra ones are skipped; a field of the wrong type skips that event (pool.go:233-237).
+    Hash lists are returned already filtered through getHashAsUint64's type rules (pool.go:270-277): the elements are
+    plain ints (the uint64 value) so that digest_events sees exactly what the Go code would append."""
     try:
-        batch = msgpack.unpackb(payload, raw=False, strict_map_key=False)
-    except Exception:
+        batch, _ = _mp_read(bytes(payload), 0)
+    except _MpError:
         return []
-    if not isinstance(batch, (list, tuple)) or len(batch) < 2 or not isinstance(batch[1], (list, tuple)):
+    if not isinstance(batch, list):
+        return []
+    n = len(batch)
+    if n >= 1 and not (isinstance(batch[0], float) or _is_int(batch[0]) or batch[0] is None):
+        return []
+    events_raw = []
+    if n >= 2:
+        if isinstance(batch[1], list):
+            events_raw = batch[1]
+        elif batch[1] is not None:
+            return []
+    if n >= 3 and not (_is_int(batch[2]) or batch[2] is None):
         return []
     out = []
-    for ev in batch[1]:
-        if not isinstance(ev, (list, tuple)) or len(ev) < 1 or not isinstance(ev[0], str):
+    for ev in events_raw:
+        if not isinstance(ev, list) or len(ev) < 1:
             continue
-        tag, f = ev[0], list(ev[1:])
-        try:
-            if tag == "BlockStored":
-                if len(f) < 4:
-                    continue
-                out.append(BlockStored(list(f[0] or []), f[1], [int(t) for t in (f[2] or [])], int(f[3] or 0),
-                                       f[4] if len(f) > 4 else None, f[5] if len(f) > 5 else None))
-            elif tag == "BlockRemoved":
-                if len(f) < 1:
-                    continue
-                out.append(BlockRemoved(list(f[0] or []), f[1] if len(f) > 1 else None))
-            elif tag == "AllBlocksCleared":
-                out.append(AllBlocksCleared())
-        except Exception:
+        tag = ev[0]
+        if isinstance(tag, (bytes, bytearray)) and not isinstance(tag, str):
+            tag = bytes(tag).decode("utf-8", "surrogateescape")
+        if not isinstance(tag, str):
             continue
+        f = ev[1:]
+
+        def medium_of(idx):
+            if len(f) <= idx or f[idx] is None:
+                return None, True
+            m = f[idx]
+            if isinstance(m, (bytes, bytearray)) and not isinstance(m, str):
+                return bytes(m).decode("utf-8", "surrogateescape"), True
+            if isinstance(m, str):
+                return str(m), True
+            return None, False
+
+        def hashes_of(v):
+            if v is None:
+                return [], True
+            if not isinstance(v, list):
+                return None, False
+            res = []
+            for x in v:
+                try:
+                    res.append(typed_hash(x))
+                except (TypeError, ValueError):
+                    continue                       # pool.go:272-275: unsupported / empty hash is skipped
+            return res, True
+
+        if tag == "BlockStored":
+            hs, ok = hashes_of(f[0]) if len(f) > 0 else ([], True)
+            if not ok:
+                continue
+            parent = None
+            parent_bad = False
+            if len(f) > 1 and f[1] is not None:
+                try:
+                    parent = typed_hash(f[1])
+                except (TypeError, ValueError):
+                    parent_bad = True
+            toks = []
+            if len(f) > 2 and f[2] is not None:
+                if not isinstance(f[2], list) or not all(_is_int(t) for t in f[2]):
+                    continue
+                toks = [int(t) & 0xFFFFFFFF for t in f[2]]
+            if len(f) > 3 and not (_is_int(f[3]) or f[3] is None):
+                continue
+            if len(f) > 4 and not (_is_int(f[4]) or f[4] is None):
+                continue
+            med, ok = medium_of(5)
+            if not ok:
+                continue
+            if parent_bad:
+                continue                           # pool.go:283-287: the whole event is skipped
+            out.append(BlockStored(hs, parent, toks, 0, None, med))
+        elif tag == "BlockRemoved":
+            hs, ok = hashes_of(f[0]) if len(f) > 0 else ([], True)
+            if not ok:
+                continue
+            med, ok = medium_of(1)
+            if not ok:
+                continue
+            out.append(BlockRemoved(hs, med))
+        elif tag == "AllBlocksCleared":
+            out.append(AllBlocksCleared())
     return out
+
+
+def medium_tier(medium):
+    """lower(Medium) or "gpu" (kvevents/pool.go:258-261).  Go's strings.ToLower folds Unicode letters (and rewrites invalid
+    UTF-8); vLLM media are ASCII ("GPU", "CPU", ...), so only ASCII letters are folded here and in the C++ host mirror."""
+    if medium is None:
+        return DEFAULT_DEVICE_TIER
+    return "".join(chr(ord(c) + 32) if "A" <= c <= "Z" else c for c in medium)
 
 
 class EventsPool:
@@ -434,7 +610,7 @@ class EventsPool:
         """digestEvents (pool.go:246-338)."""
         for ev in events:
             if isinstance(ev, BlockStored):
-                tier = ev.medium.lower() if ev.medium is not None else DEFAULT_DEVICE_TIER   # :258-261
+                tier = medium_tier(ev.medium)                                 # :258-261
                 entries = [PodEntry(pod, tier)]
                 engine_keys = []
                 for raw in ev.block_hashes:                                  # :270-277 bad hashes skipped
@@ -459,7 +635,7 @@ class EventsPool:
                     except IndexError_:
                         continue                                             # event dropped
             elif isinstance(ev, BlockRemoved):
-                tier = ev.medium.lower() if ev.medium is not None else DEFAULT_DEVICE_TIER
+                tier = medium_tier(ev.medium)
                 entries = [PodEntry(pod, tier)]
                 for raw in ev.block_hashes:                                  # :317-330
                     try:
