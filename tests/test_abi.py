@@ -29,6 +29,23 @@ def test_header_symbols_all_exported_and_bound():
     assert sorted(_native.SYMBOLS) == names
 
 
+def test_host_mirror_symbols_exported_and_bound():
+    from kvidx import host
+    src = open(os.path.join(ROOT, "include", "kvidx_host.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(kvhost_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) >= 17
+    L = C.CDLL(_native.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libkvidx.so does not export %s" % n
+    assert sorted(host.SYMBOLS) == names
+    h = host.HostIndexer(no_device=True)                  # host-only instance works without a GPU ...
+    assert h.pod_id("pod-a") == 0 and h.pod_id("pod-b") == 1 and h.pod_id("pod-a") == 0 and h.tier_id("CPU") == 1
+    with pytest.raises(kvidx.KvidxError) as ei:           # ... but scoring does not silently fall back to the CPU
+        h.get_pod_scores(list(range(32)), "m")
+    assert ei.value.code == kvidx.ECUDA and "no CPU fallback" in str(ei.value)
+
+
 def test_abi_version_and_struct_layout():
     L = kvidx.load()
     assert L.kvidx_abi_version() == 1
