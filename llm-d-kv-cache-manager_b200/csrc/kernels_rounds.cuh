@@ -28,6 +28,8 @@ namespace kvx {
 constexpr int kRoundBlocks = 32;         // blocks hashed per prompt per round (== lanes per warp in kernel P)
 constexpr int kHashThreads = 256;
 constexpr int kProbeThreads = 256;
+constexpr int kGroupThreads = 256;
+constexpr uint32_t kRoleSelf = 0xffffffffu;
 
 struct __align__(8) PromptState {        // walk state carried between rounds (only for prompts that continue)
     double sc[kMaxEnt];
@@ -47,6 +49,13 @@ struct RoundBufs {
     uint64_t* keys;                      // [kRoundBlocks][n_prompts] keys of the current round, block-major: key of
                                          // block j of list slot i at keys[j * n_prompts + i] (coalesced both ways)
     uint32_t* nbr;                       // [n_act] per list slot: blocks hashed this round | (more blocks follow) << 8
+    // chunk-level prefix sharing (group_round_kernel): a prompt whose chain state and next chunk of tokens equal another
+    // prompt's reuses that prompt's keys instead of hashing them again
+    uint32_t* role;                      // [n_act] kRoleSelf: hashes its own chunk; else the list slot whose keys it shares
+    uint32_t* hl;                        // [n_act] compacted list of slots that hash this round
+    unsigned int* n_hl;                  // its length (zeroed before every round)
+    uint32_t* map;                       // leader election: bucket -> slot (kRoleSelf = empty), cleared before every round
+    uint32_t map_mask;
     PromptState* pst;                    // per prompt
 };
 
@@ -57,6 +66,101 @@ template <int BS> struct HashSmem {
     unsigned char tok[kHashThreads / 32][2][32 * kRow];
 };
 
+// ---- kernel G: who hashes, who shares ----------------------------------------------------------------------
+// One warp per list slot.  The warp reads the prompt's next chunk (<= 32 blocks = 2 KB, coalesced), folds it into a
+// 64-bit fingerprint, and lane 0 tries to claim bucket hash(chain state, fingerprint) of a small map.  The winner
+// hashes (it is a leader); a loser compares its chain state and its chunk, 16 bytes per lane, against the bucket
+// owner's -- equal means every key of the chunk is equal too (same parent, same tokens), so it only records whose
+// keys to read.  The comparison is exact, so map collisions and fingerprint collisions can only cost sharing, never
+// correctness.  Slots that hash are compacted into `hl` (one atomic per CTA iteration).
+template <int BS>
+__global__ void __launch_bounds__(kGroupThreads)
+group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int dedup) {
+    __shared__ uint32_t s_self[kGroupThreads / 32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int n_act = rb.n_act[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
+    constexpr int WPB = kGroupThreads / 32;
+    for (unsigned int i0 = blockIdx.x * WPB; i0 < n_act; i0 += gridDim.x * WPB) {
+        const unsigned int i = i0 + wid;
+        bool self = false;
+        if (i < n_act) {
+            const uint32_t p = rb.act[cur][i];
+            const int64_t b = a.tok_off[p] - a.tok_base, e = a.tok_off[p + 1] - a.tok_base;
+            const int64_t nblk = (e - b) / BS;
+            const int64_t first = (int64_t)round * kRoundBlocks;
+            const int nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
+            if (lane == 0) rb.nbr[i] = (uint32_t)nb | ((first + nb < nblk) ? 0x100u : 0u);
+            uint32_t role = kRoleSelf;
+            self = nb > 0;
+            if (nb > 0 && dedup) {
+                const uint32_t* src = a.tok + b + first * BS;
+                const int nwords = nb * BS;                               // tokens in the chunk
+                const uint64_t hprev = round == 0 ? t.init_hash : rb.hstate[p];
+                const bool al = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+                // fingerprint: position-salted mix of every 16-byte piece, xor-reduced over the warp
+                uint64_t f = 0;
+                uint4 mine[kRoundBlocks * BS / 128];                      // this lane's pieces (4 for 2 KB)
+#pragma unroll
+                for (int c = 0; c < kRoundBlocks * BS / 128; ++c) {
+                    const int w0 = (c * 32 + lane) * 4;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (w0 < nwords) {
+                        if (al) v = __ldg(reinterpret_cast<const uint4*>(src + w0));
+                        else { v.x = __ldg(src + w0); v.y = __ldg(src + w0 + 1); v.z = __ldg(src + w0 + 2); v.w = __ldg(src + w0 + 3); }
+                        f ^= mix64((((uint64_t)v.y << 32) | v.x) + 0x9E3779B97F4A7C15ull * (uint64_t)(w0 + 1)) ^
+                             mix64((((uint64_t)v.w << 32) | v.z) + 0xC2B2AE3D27D4EB4Full * (uint64_t)(w0 + 3));
+                    }
+                    mine[c] = v;
+                }
+#pragma unroll
+                for (int o = 16; o; o >>= 1) f ^= __shfl_xor_sync(0xffffffffu, f, o);
+                const uint64_t key = mix64(f ^ (hprev * 0xFF51AFD7ED558CCDull) ^ (uint64_t)nb);
+                uint32_t cand = kRoleSelf;
+                if (lane == 0) cand = atomicCAS(&rb.map[(uint32_t)key & rb.map_mask], kRoleSelf, i);
+                cand = __shfl_sync(0xffffffffu, cand, 0);
+                if (cand != kRoleSelf && cand != i) {
+                    // verify against the bucket owner: same chain state, at least as many blocks, identical tokens
+                    const uint32_t pl = rb.act[cur][cand];
+                    const int64_t bl = a.tok_off[pl] - a.tok_base, el = a.tok_off[pl + 1] - a.tok_base;
+                    const int64_t nbl = (el - bl) / BS - first;
+                    bool ok = nbl >= nb && (round == 0 || rb.hstate[pl] == hprev);
+                    const uint32_t* sl = a.tok + bl + first * BS;
+                    const bool all = (reinterpret_cast<uintptr_t>(sl) & 15u) == 0;
+#pragma unroll
+                    for (int c = 0; c < kRoundBlocks * BS / 128; ++c) {
+                        const int w0 = (c * 32 + lane) * 4;
+                        if (ok && w0 < nwords) {
+                            uint4 v;
+                            if (all) v = __ldg(reinterpret_cast<const uint4*>(sl + w0));
+                            else { v.x = __ldg(sl + w0); v.y = __ldg(sl + w0 + 1); v.z = __ldg(sl + w0 + 2); v.w = __ldg(sl + w0 + 3); }
+                            ok = ((v.x ^ mine[c].x) | (v.y ^ mine[c].y) | (v.z ^ mine[c].z) | (v.w ^ mine[c].w)) == 0u;
+                        }
+                    }
+                    if (__all_sync(0xffffffffu, ok)) { role = cand; self = false; }
+                }
+            }
+            if (lane == 0) rb.role[i] = role;
+        }
+        // compact the slots that hash: one atomic per CTA iteration, list order kept inside it
+        if (lane == 0) s_self[wid] = self ? 1u : 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t c = 0;
+            for (int w = 0; w < WPB; ++w) c += s_self[w];
+            s_base = c ? atomicAdd(rb.n_hl, c) : 0u;
+        }
+        __syncthreads();
+        if (self && lane == 0) {
+            uint32_t before = 0;
+            for (int w = 0; w < wid; ++w) before += s_self[w];
+            rb.hl[s_base + before] = i;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- kernel H ---------------------------------------------------------------------------------
 template <int BS>
 __global__ void __launch_bounds__(kHashThreads, 4)
@@ -66,12 +170,11 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
     using SM = HashSmem<BS>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned int n_act = rb.n_act[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
+    const unsigned int n_hl = *rb.n_hl;                                   // slots that hash this round (kernel G)
     const unsigned int total_warps = gridDim.x * (kHashThreads / 32);
-    for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
-        const unsigned int i = w * 32u + lane;                            // slot in the active list
-        const bool have = i < n_act;
+    for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_hl; w += total_warps) {
+        const bool have = w * 32u + lane < n_hl;
+        const unsigned int i = have ? rb.hl[w * 32u + lane] : 0u;        // slot in the active list
         const uint32_t p = have ? rb.act[cur][i] : 0u;
         int nb = 0;                                                      // blocks of this prompt in this round
         const uint32_t* src = nullptr;
@@ -82,7 +185,6 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
             const int64_t nblk = (e - b) / BS;
             const int64_t first = (int64_t)round * kRoundBlocks;
             nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
-            rb.nbr[i] = (uint32_t)nb | ((first + nb < nblk) ? 0x100u : 0u);
             src = a.tok + b + first * BS;
             aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
             h = round == 0 ? t.init_hash : rb.hstate[p];
@@ -137,7 +239,6 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
         }
         cp_async_wait<0>();
         __syncwarp();
-        if (have && nb > 0) rb.hstate[p] = h;
     }
 }
 
@@ -188,6 +289,9 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         const int nb = (int)(meta & 63u);
         const bool has_more = (meta >> 8) & 1u;
         const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
+        const uint32_t rl = have ? rb.role[i] : kRoleSelf;
+        const unsigned int ks = rl == kRoleSelf ? i : rl;       // list slot whose keys this prompt reads (its own or its leader's)
+        uint64_t lastkey = 0;
         uint32_t k = 0, alive = 0;
         uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0;      // last scored pattern
         if (round > 0 && have) {
@@ -208,12 +312,12 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         const ReqSlot* base = t.req;                           // table (shard) of the current block's key
         uint4 A0 = {0, 0, 0, 0}, B0 = {0, 0, 0, 0}, A1 = {0, 0, 0, 0}, B1 = {0, 0, 0, 0};
         if (!done) {
-            key = rb.keys[i];
+            key = rb.keys[ks];
             const uint64_t hm = home_of(key, mdl);
             base = t.req_peer[shard_of(hm, t.shard_bits)]; slot = hm & t.req_mask & ~1ull;
             ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
         }
-        uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + i] : 0ull;                         // key of block j+1
+        uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + ks] : 0ull;                         // key of block j+1
         for (int j = 0; j < nb_max; ++j) {
             // next block's pair is requested before this block is scored; keys are read one iteration ahead of their use
             uint64_t nkey = key1, nslot = 0;
@@ -225,8 +329,9 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 nbase = t.req_peer[shard_of(hm, t.shard_bits)]; nslot = hm & t.req_mask & ~1ull;
                 ld_slot_pair(nbase + nslot, peer, nA0, nB0, nA1, nB1);
             }
-            key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + i] : 0ull;
+            key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + ks] : 0ull;
             if (!done && j < nb) {
+                lastkey = key;
                 uint4 A = A0, B = B0;
                 bool hit = slot_matches(A, B, key, mdl);
                 if (!hit && meta_state(B.w) != kStateEmpty) {
@@ -298,6 +403,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             if (more) {
                 rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
                 PromptState& ps = rb.pst[p];
+                rb.hstate[p] = lastkey;                          // chain state for the next round (key of this round's last block)
                 ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
                 ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
                 for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; ps.bt[q] = W.bt[q][lane]; }

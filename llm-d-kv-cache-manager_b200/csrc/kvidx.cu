@@ -97,7 +97,8 @@ struct kvidx {
     int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
-    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort;
+    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map;
+    int rounds_dedup = 1;          // chunk-level prefix sharing in the round pipeline
     int sort_prefix = 1;           // sort the batch by first-block fingerprint before the rounds
     int rounds_overlap = 1;        // run the two halves of a large batch on two streams
     int64_t rounds_overlap_min = 65536;
@@ -209,7 +210,9 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
                         int64_t max_blocks) {
     CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(64));
     CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState)));
-    CK(x->r_nbr.need((size_t)n * 4));
+    CK(x->r_nbr.need((size_t)n * 4)); CK(x->r_role.need((size_t)n * 4)); CK(x->r_hl.need((size_t)n * 4));
+    const uint64_t map_slots = pow2ceil((uint64_t)std::max<int64_t>(4 * n, 1024));
+    CK(x->r_map.need(map_slots * 4 * 2));
     const bool overlap = x->rounds_overlap && n >= x->rounds_overlap_min;
     const int64_t nA = overlap ? ((n / 2 + 31) & ~31ll) : n, nB = n - nA;
     unsigned int* cnt = x->r_cnt.as<unsigned int>();
@@ -221,6 +224,9 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         rb[hlf].n_act = cnt + 2 * hlf;
         rb[hlf].hstate = x->r_hstate.as<uint64_t>(); rb[hlf].pst = x->r_pst.as<PromptState>();
         rb[hlf].keys = x->r_keys.as<uint64_t>() + off; rb[hlf].nbr = x->r_nbr.as<uint32_t>() + off;
+        rb[hlf].role = x->r_role.as<uint32_t>() + off; rb[hlf].hl = x->r_hl.as<uint32_t>() + off;
+        rb[hlf].n_hl = cnt + 8 + hlf;
+        rb[hlf].map = x->r_map.as<uint32_t>() + (hlf ? map_slots : 0); rb[hlf].map_mask = (uint32_t)(map_slots - 1);
     }
     ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
     CK(cudaMemsetAsync(x->r_cnt.p, 0, 64, st));
@@ -254,6 +260,10 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         const int cur = (int)(r & 1);
         for (int hlf = 0; hlf < nh; ++hlf) {
             const int64_t m = hlf ? nB : nA;
+            CK(cudaMemsetAsync(rb[hlf].map, 0xff, map_slots * 4, strm[hlf]));
+            CK(cudaMemsetAsync(rb[hlf].n_hl, 0, 4, strm[hlf]));
+            const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads / 32 - 1) / (kGroupThreads / 32), (int64_t)x->sm_count * 8);
+            group_round_kernel<16><<<ggrid, kGroupThreads, 0, strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r, x->rounds_dedup);
             const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * per_sm_h);
             hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
         }
@@ -262,7 +272,7 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
             const unsigned pgrid = (unsigned)std::min<int64_t>((m + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * per_sm_p);
             probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
         }
-        x->launches += 2 * nh;
+        x->launches += 3 * nh;
     }
     CK(cudaGetLastError());
     if (nh == 2) { CK(cudaEventRecord(x->ev_join, x->aux_stream)); CK(cudaStreamWaitEvent(st, x->ev_join, 0)); }
@@ -550,6 +560,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
     if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
     if (rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = score_tuned_init();
@@ -569,7 +580,7 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_done[i]) cudaEventDestroy(x->ev_done[i]);
         if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]);
     }
-    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release();
+    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release(); x->r_role.release(); x->r_hl.release(); x->r_map.release();
     x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
     if (x->tv.req) cudaFree(x->tv.req);
     if (x->tv.eng) cudaFree(x->tv.eng);

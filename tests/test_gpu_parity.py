@@ -276,12 +276,15 @@ def _select_path(monkeypatch, path):
     elif path == "rounds-nosort":
         monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
         monkeypatch.setenv("KVIDX_SORT_PREFIX", "0")
+    elif path == "rounds-nodedup":
+        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
+        monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "0")
     else:
         monkeypatch.setenv("KVIDX_SCORE_PATH", path)
         monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP", "0")
 
 
-PATHS = ["v1", "fused", "rounds", "rounds2", "rounds-nosort"]
+PATHS = ["v1", "fused", "rounds", "rounds2", "rounds-nosort", "rounds-nodedup"]
 
 
 @pytest.mark.parametrize("kernel", PATHS)
@@ -337,6 +340,54 @@ def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
     for i in range(0, len(prompts), 97):
         got = {int(sp_p[i, j]): float(sp_s[i, j]) for j in range(sp_c[i])}
         assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
+
+
+@pytest.mark.parametrize("kernel", ["rounds", "rounds2", "rounds-nosort"])
+def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
+    """The round pipeline lets a prompt reuse another prompt's keys when chain state and the next 32-block chunk are
+    identical.  Few documents, thousands of prompts: exact duplicates, prefixes of every length (so the shared chunk is
+    shorter than the leader's), divergence at every position inside a chunk, unaligned starts, per-prompt models and
+    filters.  Everything bit-exact against the oracle."""
+    _select_path(monkeypatch, kernel)
+    rng = np.random.default_rng(77)
+    BS, T, ND = 16, 2048 + 160, 6                       # 138 blocks: four full rounds and a 10-block one
+    docs = rng.integers(0, 50000, size=(ND, T), dtype=np.uint32)
+    ix, co = _index_pair(capacity=1 << 12, max_pods=16)
+    for d in range(ND):
+        keys = ix.hash_keys(docs[d], np.array([0, T], np.int64))[0]
+        nb = len(keys) if d % 2 == 0 else int(rng.integers(20, len(keys)))      # some documents only partly cached
+        for pod in rng.choice(16, size=3, replace=False):
+            pt = [(int(pod) << 4) | int(rng.integers(0, 2))]
+            eng = (keys[:nb] ^ np.uint64(0x5555)).astype(np.uint64)
+            assert ix.add(0, eng, keys[:nb], pt) == 0
+            co.add(0, eng, keys[:nb], pt)
+    prompts = []
+    for i in range(4000):
+        d = docs[int(rng.integers(0, ND))]
+        kind = i % 5
+        if kind == 0:
+            pr = d.copy()                                                        # exact duplicate of a document
+        elif kind == 1:
+            pr = d[: int(rng.integers(0, T + 1))].copy()                         # a prefix, any length
+        elif kind == 2:
+            pr = d.copy(); pr[int(rng.integers(0, T)):] = rng.integers(0, 50000)  # diverges somewhere
+        elif kind == 3:
+            pr = d.copy(); pr[int(rng.integers(0, T))] ^= np.uint32(1)            # single-token difference
+        else:
+            pr = np.concatenate([d[: BS * int(rng.integers(0, T // BS))], rng.integers(0, 50000, size=int(rng.integers(0, 700)), dtype=np.uint32)])
+        prompts.append(pr.astype(np.uint32))
+    tok, off = csr(prompts)
+    assert (off[:-1] % 4 != 0).any()
+    s_t, h_t = ix.score_batch(tok, off)
+    s_o, h_o, _, _ = co.score_batch(tok, off, n_threads=4)
+    assert np.array_equal(h_t, h_o) and np.array_equal(s_t, s_o), np.argwhere(s_t != s_o)[:5]
+    assert (s_o.max(axis=1) >= 128).any()               # some walks go through every round
+    fm = np.zeros((len(prompts), ix.filter_words), np.uint64)
+    for i in range(0, len(prompts), 3):
+        fm[i] = filter_mask(rng.choice(16, size=int(rng.integers(1, 4)), replace=False).tolist(), ix.filter_words)
+    s_t, _ = ix.score_batch(tok, off, filter_mask=fm)
+    s_o, _, _, _ = co.score_batch(tok, off, filter_mask=fm, n_threads=4)
+    assert np.array_equal(s_t, s_o), np.argwhere(s_t != s_o)[:5]
 
 
 def test_rebuild_after_tombstones():
