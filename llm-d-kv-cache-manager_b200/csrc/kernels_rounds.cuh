@@ -42,22 +42,30 @@ struct __align__(8) PromptState {        // walk state carried between rounds (o
     uint8_t pad2[2];
 };
 
+constexpr int kMaxParts = 4;              // the sorted batch runs as up to this many independent parts on their own streams
+
 struct RoundBufs {
-    uint32_t* act[2];                    // active prompt lists (ping-pong)
+    uint32_t* act[2];                    // live prompt lists (ping-pong)
     unsigned int* n_act;                 // [2] list lengths
-    uint64_t* hstate;                    // chain hash after the last hashed block, per prompt
-    uint64_t* keys;                      // [kRoundBlocks][n_prompts] keys of the current round, block-major: key of
-                                         // block j of list slot i at keys[j * n_prompts + i] (coalesced both ways)
-    uint32_t* nbr;                       // [n_act] per list slot: blocks hashed this round | (more blocks follow) << 8
-    // chunk-level prefix sharing (group_round_kernel): a prompt whose chain state and next chunk of tokens equal another
-    // prompt's reuses that prompt's keys instead of hashing them again
-    uint32_t* role;                      // [n_act] kRoleSelf: hashes its own chunk; else the list slot whose keys it shares
-    uint32_t* hl;                        // [n_act] compacted list of slots that hash this round
-    unsigned int* n_hl;                  // its length (zeroed before every round)
-    uint32_t* map;                       // leader election: bucket -> slot (kRoleSelf = empty), cleared before every round
+    uint64_t* hstate;                    // per prompt: chain hash after the last block of the previous round
+    uint32_t* src;                       // per prompt: the prompt whose PromptState (previous round's buffer) is this prompt's
+                                         // walk state -- itself, or the representative of the class it was in
+    PromptState* pst[2];                 // per prompt, by round parity (round r reads [r&1 ^ 1], writes [r&1])
+    uint64_t* keys;                      // [kRoundBlocks][n_prompts] keys of the current round, block-major, by position in
+                                         // the representative list: key of block j of entry a at keys[j * n_prompts + a]
+    uint32_t* nbr;                       // [n_act] per live slot: blocks in this round | (more blocks follow) << 8
+    // prefix classes (group_round_kernel): live prompts with the same walk state, model and filter whose next chunk of
+    // tokens is identical get identical keys, probes, scores and fate this round.  One representative per class is
+    // hashed and walked; the others wait in the follower list and take the representative's outcome.
+    uint32_t* role;                      // [n_act] kRoleSelf: representative (or alone); else the live slot of its representative
+    uint8_t* fate;                       // [n_act] written for representatives by kernel P: kFateMore / kFateDone
+    uint32_t* hl;                        // [n_act] representative list (live slots), compacted
+    uint32_t* fl;                        // [n_act] follower list (live slots), compacted
+    unsigned int* n_hl;                  // n_hl[0] = representatives, n_hl[1] = followers (zeroed before every round)
+    uint32_t* map;                       // class election: bucket -> live slot (kRoleSelf = empty), cleared before every round
     uint32_t map_mask;
-    PromptState* pst;                    // per prompt
 };
+constexpr uint8_t kFateMore = 1, kFateDone = 2;
 
 constexpr int kHashChunk = 1;            // blocks staged per copy step (2 = 128-byte accesses was measured: fewer, longer DRAM
                                          // accesses but only 24 resident warps/SM -> 6 % slower; the kernel is pipe bound)
@@ -66,98 +74,170 @@ template <int BS> struct HashSmem {
     unsigned char tok[kHashThreads / 32][2][32 * kRow];
 };
 
-// ---- kernel G: who hashes, who shares ----------------------------------------------------------------------
-// One warp per list slot.  The warp reads the prompt's next chunk (<= 32 blocks = 2 KB, coalesced), folds it into a
-// 64-bit fingerprint, and lane 0 tries to claim bucket hash(chain state, fingerprint) of a small map.  The winner
-// hashes (it is a leader); a loser compares its chain state and its chunk, 16 bytes per lane, against the bucket
-// owner's -- equal means every key of the chunk is equal too (same parent, same tokens), so it only records whose
-// keys to read.  The comparison is exact, so map collisions and fingerprint collisions can only cost sharing, never
-// correctness.  Slots that hash are compacted into `hl` (one atomic per CTA iteration).
+// ---- kernel G: prefix classes ------------------------------------------------------------------------------
+// A warp takes 32 live slots.  Metadata is lane-parallel; each prompt's next chunk (<= 32 blocks = 2 KB) is then read by
+// the whole warp (coalesced) and folded into a 64-bit fingerprint.  Lane-parallel again, every prompt tries to claim
+// bucket hash(state source, chain state, model, fingerprint) of a small map: the winner represents the class; a loser
+// compares itself with the bucket owner -- state source, chain state, block count, model, filter row, and the chunk
+// token by token (warp-wide, 16 bytes per lane).  Only an exact match joins the class, so fingerprint and bucket
+// collisions can cost sharing, never correctness.  Representatives and followers are compacted into two lists.
+__device__ __forceinline__ void chunk_load(const uint32_t* sp, int nw, int lane, uint4 (&v)[4]) {
+    const bool al = (reinterpret_cast<uintptr_t>(sp) & 15u) == 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int w0 = (c * 32 + lane) * 4;
+        v[c] = make_uint4(0, 0, 0, 0);
+        if (w0 < nw) {
+            if (al) v[c] = __ldg(reinterpret_cast<const uint4*>(sp + w0));
+            else { v[c].x = __ldg(sp + w0); v[c].y = __ldg(sp + w0 + 1); v[c].z = __ldg(sp + w0 + 2); v[c].w = __ldg(sp + w0 + 3); }
+        }
+    }
+}
+
 template <int BS>
 __global__ void __launch_bounds__(kGroupThreads)
 group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int dedup) {
-    __shared__ uint32_t s_self[kGroupThreads / 32];
-    __shared__ uint32_t s_base;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    static_assert(BS == 16 && kRoundBlocks == 32, "a chunk is 4 x 32 lanes x 16 bytes");
+    const int lane = threadIdx.x & 31;
     const unsigned int n_act = rb.n_act[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
-    constexpr int WPB = kGroupThreads / 32;
-    for (unsigned int i0 = blockIdx.x * WPB; i0 < n_act; i0 += gridDim.x * WPB) {
-        const unsigned int i = i0 + wid;
-        bool self = false;
-        if (i < n_act) {
-            const uint32_t p = rb.act[cur][i];
+    const unsigned int total_warps = gridDim.x * (kGroupThreads / 32);
+    for (unsigned int w = blockIdx.x * (kGroupThreads / 32) + (threadIdx.x >> 5); w * 32u < n_act; w += total_warps) {
+        const unsigned int i = w * 32u + lane;
+        const bool have = i < n_act;
+        uint32_t p = 0, srcp = kRoleSelf, mdl = a.model0;
+        int nb = 0; bool more = false;
+        uint64_t hprev = t.init_hash;
+        const uint32_t* tp = a.tok;
+        int64_t first = (int64_t)round * kRoundBlocks;
+        if (have) {
+            p = rb.act[cur][i];
             const int64_t b = a.tok_off[p] - a.tok_base, e = a.tok_off[p + 1] - a.tok_base;
             const int64_t nblk = (e - b) / BS;
-            const int64_t first = (int64_t)round * kRoundBlocks;
-            const int nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
-            if (lane == 0) rb.nbr[i] = (uint32_t)nb | ((first + nb < nblk) ? 0x100u : 0u);
-            uint32_t role = kRoleSelf;
-            self = nb > 0;
-            if (nb > 0 && dedup) {
-                const uint32_t* src = a.tok + b + first * BS;
-                const int nwords = nb * BS;                               // tokens in the chunk
-                const uint64_t hprev = round == 0 ? t.init_hash : rb.hstate[p];
-                const bool al = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-                // fingerprint: position-salted mix of every 16-byte piece, xor-reduced over the warp
-                uint64_t f = 0;
-                uint4 mine[kRoundBlocks * BS / 128];                      // this lane's pieces (4 for 2 KB)
-#pragma unroll
-                for (int c = 0; c < kRoundBlocks * BS / 128; ++c) {
-                    const int w0 = (c * 32 + lane) * 4;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (w0 < nwords) {
-                        if (al) v = __ldg(reinterpret_cast<const uint4*>(src + w0));
-                        else { v.x = __ldg(src + w0); v.y = __ldg(src + w0 + 1); v.z = __ldg(src + w0 + 2); v.w = __ldg(src + w0 + 3); }
-                        f ^= mix64((((uint64_t)v.y << 32) | v.x) + 0x9E3779B97F4A7C15ull * (uint64_t)(w0 + 1)) ^
-                             mix64((((uint64_t)v.w << 32) | v.z) + 0xC2B2AE3D27D4EB4Full * (uint64_t)(w0 + 3));
-                    }
-                    mine[c] = v;
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) f ^= __shfl_xor_sync(0xffffffffu, f, o);
-                const uint64_t key = mix64(f ^ (hprev * 0xFF51AFD7ED558CCDull) ^ (uint64_t)nb);
-                uint32_t cand = kRoleSelf;
-                if (lane == 0) cand = atomicCAS(&rb.map[(uint32_t)key & rb.map_mask], kRoleSelf, i);
-                cand = __shfl_sync(0xffffffffu, cand, 0);
-                if (cand != kRoleSelf && cand != i) {
-                    // verify against the bucket owner: same chain state, at least as many blocks, identical tokens
-                    const uint32_t pl = rb.act[cur][cand];
-                    const int64_t bl = a.tok_off[pl] - a.tok_base, el = a.tok_off[pl + 1] - a.tok_base;
-                    const int64_t nbl = (el - bl) / BS - first;
-                    bool ok = nbl >= nb && (round == 0 || rb.hstate[pl] == hprev);
-                    const uint32_t* sl = a.tok + bl + first * BS;
-                    const bool all = (reinterpret_cast<uintptr_t>(sl) & 15u) == 0;
-#pragma unroll
-                    for (int c = 0; c < kRoundBlocks * BS / 128; ++c) {
-                        const int w0 = (c * 32 + lane) * 4;
-                        if (ok && w0 < nwords) {
-                            uint4 v;
-                            if (all) v = __ldg(reinterpret_cast<const uint4*>(sl + w0));
-                            else { v.x = __ldg(sl + w0); v.y = __ldg(sl + w0 + 1); v.z = __ldg(sl + w0 + 2); v.w = __ldg(sl + w0 + 3); }
-                            ok = ((v.x ^ mine[c].x) | (v.y ^ mine[c].y) | (v.z ^ mine[c].z) | (v.w ^ mine[c].w)) == 0u;
-                        }
-                    }
-                    if (__all_sync(0xffffffffu, ok)) { role = cand; self = false; }
-                }
+            nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
+            more = first + nb < nblk;
+            rb.nbr[i] = (uint32_t)nb | (more ? 0x100u : 0u);
+            tp = a.tok + b + first * BS;
+            if (round > 0) { srcp = rb.src[p]; hprev = rb.hstate[p]; }
+            if (a.model) mdl = a.model[p];
+        }
+        const bool cls = have && nb > 0 && dedup;
+        // Does the prompt equal its predecessor in the list?  (The list is sorted by prefix, so mostly yes.)  Everything
+        // but the tokens lane-parallel here; the tokens as the chunks stream by below.
+        uint64_t fsum = 0;
+        if (cls && round == 0 && a.filter) { const uint64_t* fr = a.filter + (int64_t)p * t.filter_words; for (uint32_t x = 0; x < t.filter_words; ++x) fsum = (fsum ^ fr[x]) * 0x9E3779B97F4A7C15ull; }
+        bool eqm;
+        {
+            const int nb_u = __shfl_up_sync(0xffffffffu, nb, 1); const int more_u = __shfl_up_sync(0xffffffffu, (int)more, 1);
+            const uint32_t mdl_u = __shfl_up_sync(0xffffffffu, mdl, 1), src_u = __shfl_up_sync(0xffffffffu, srcp, 1);
+            const uint64_t h_u = __shfl_up_sync(0xffffffffu, hprev, 1), f_u = __shfl_up_sync(0xffffffffu, fsum, 1);
+            const int cls_u = __shfl_up_sync(0xffffffffu, (int)cls, 1);
+            eqm = cls && lane > 0 && cls_u && nb_u == nb && more_u == (int)more && mdl_u == mdl && src_u == srcp && h_u == hprev && f_u == fsum;
+            if (eqm && round == 0 && a.filter) {       // equal filter fingerprints: compare the rows themselves
+                const uint32_t pu = rb.act[cur][i - 1];
+                const uint64_t* fa = a.filter + (int64_t)p * t.filter_words; const uint64_t* fb = a.filter + (int64_t)pu * t.filter_words;
+                for (uint32_t x = 0; x < t.filter_words; ++x) eqm = eqm && fa[x] == fb[x];
             }
-            if (lane == 0) rb.role[i] = role;
         }
-        // compact the slots that hash: one atomic per CTA iteration, list order kept inside it
-        if (lane == 0) s_self[wid] = self ? 1u : 0u;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t c = 0;
-            for (int w = 0; w < WPB; ++w) c += s_self[w];
-            s_base = c ? atomicAdd(rb.n_hl, c) : 0u;
+        // chunks, one prompt at a time, the next one in flight while this one is compared with the previous one (still in
+        // registers) and -- only if it differs -- folded into a fingerprint for the election
+        uint32_t f0 = 0, f1 = 0;
+        bool eqprev = false;                         // same class as the previous list entry
+        uint32_t todo = __ballot_sync(0xffffffffu, cls);
+        const uint32_t eqm_mask = __ballot_sync(0xffffffffu, eqm);
+        uint4 v[4], vn[4], vp[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vp[c] = make_uint4(0, 0, 0, 0);
+        int q = todo ? __ffs(todo) - 1 : -1, qprev = -2;
+        if (q >= 0) chunk_load(reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, q)),
+                               __shfl_sync(0xffffffffu, nb, q) * BS, lane, v);
+        while (q >= 0) {
+            todo &= todo - 1;
+            const int qn = todo ? __ffs(todo) - 1 : -1;
+            if (qn >= 0) chunk_load(reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, qn)),
+                                    __shfl_sync(0xffffffffu, nb, qn) * BS, lane, vn);
+            bool same = false;
+            if (qprev == q - 1 && ((eqm_mask >> q) & 1u)) {          // warp-uniform
+                uint32_t d = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) d |= (v[c].x ^ vp[c].x) | (v[c].y ^ vp[c].y) | (v[c].z ^ vp[c].z) | (v[c].w ^ vp[c].w);
+                same = __all_sync(0xffffffffu, d == 0u);
+            }
+            if (same) { if (lane == q) eqprev = true; }
+            else {
+                uint32_t a0 = 0, a1 = 0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t w0 = (uint32_t)(c * 32 + lane) * 4u;
+                    uint32_t x = (v[c].x ^ (w0 * 0x9E3779B1u + 0x7F4A7C15u)) * 0x85EBCA6Bu; x = (x ^ v[c].y) * 0xC2B2AE35u; x ^= x >> 15;
+                    uint32_t y = (v[c].z ^ (w0 * 0x7FEB352Du + 0x165667B1u)) * 0x846CA68Bu; y = (y ^ v[c].w) * 0x9E3779B1u; y ^= y >> 13;
+                    a0 ^= x + y; a1 ^= x * 0x27D4EB2Fu ^ y;
+                }
+                a0 = __reduce_xor_sync(0xffffffffu, a0);
+                a1 = __reduce_xor_sync(0xffffffffu, a1);
+                if (lane == q) { f0 = a0; f1 = a1; }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { vp[c] = v[c]; v[c] = vn[c]; }
+            qprev = q; q = qn;
         }
-        __syncthreads();
-        if (self && lane == 0) {
-            uint32_t before = 0;
-            for (int w = 0; w < wid; ++w) before += s_self[w];
-            rb.hl[s_base + before] = i;
+        // election among the prompts that differ from their predecessor
+        uint32_t cand = kRoleSelf;
+        if (cls && !eqprev) {
+            const uint64_t key = mix64((((uint64_t)f1 << 32) | f0) ^ (hprev * 0xFF51AFD7ED558CCDull) ^ ((uint64_t)srcp << 17) ^ (uint64_t)(nb | (more ? 64 : 0)) ^
+                                       ((uint64_t)mdl * 0xC2B2AE3D27D4EB4Full) ^ fsum);
+            cand = atomicCAS(&rb.map[(uint32_t)key & rb.map_mask], kRoleSelf, i);
         }
-        __syncthreads();
+        // a loser checks everything but the tokens lane-parallel ...
+        bool okm = false;
+        const uint32_t* lp = a.tok;
+        if (cand != kRoleSelf) {
+            const uint32_t pl = rb.act[cur][cand];
+            const int64_t bl = a.tok_off[pl] - a.tok_base, el = a.tok_off[pl + 1] - a.tok_base;
+            const int64_t nblk_l = (el - bl) / BS;
+            const int nbl = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk_l - first));
+            okm = nbl == nb && (first + nbl < nblk_l) == more && (a.model ? a.model[pl] : a.model0) == mdl;
+            if (round > 0) okm = okm && rb.src[pl] == srcp && rb.hstate[pl] == hprev;
+            else if (a.filter) {
+                const uint64_t* fa = a.filter + (int64_t)p * t.filter_words; const uint64_t* fb = a.filter + (int64_t)pl * t.filter_words;
+                for (uint32_t x = 0; x < t.filter_words; ++x) okm = okm && fa[x] == fb[x];
+            }
+            lp = a.tok + bl + first * BS;
+        }
+        // ... and the tokens warp-wide
+        bool shared = false;
+        uint32_t vm = __ballot_sync(0xffffffffu, okm);
+        while (vm) {
+            const int l = __ffs(vm) - 1; vm &= vm - 1;
+            const uint32_t* s1 = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, l));
+            const uint32_t* s2 = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)lp, l));
+            const int nw = __shfl_sync(0xffffffffu, nb, l) * BS;
+            chunk_load(s1, nw, lane, v);
+            chunk_load(s2, nw, lane, vn);
+            uint32_t d = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) d |= (v[c].x ^ vn[c].x) | (v[c].y ^ vn[c].y) | (v[c].z ^ vn[c].z) | (v[c].w ^ vn[c].w);
+            const bool same = __all_sync(0xffffffffu, d == 0u);
+            if (lane == l) shared = same;
+        }
+        // a prompt equal to its predecessor takes the class of the nearest preceding prompt that went through the election
+        {
+            const uint32_t heads = ~__ballot_sync(0xffffffffu, eqprev);            // lane 0 is always a head
+            const int hd = 31 - __clz(heads & ((2u << lane) - 1u));
+            const uint32_t cand_h = __shfl_sync(0xffffffffu, cand, hd);
+            const int shared_h = __shfl_sync(0xffffffffu, (int)shared, hd);
+            const unsigned int i_h = __shfl_sync(0xffffffffu, i, hd);
+            if (eqprev) { shared = true; cand = shared_h ? cand_h : i_h; }
+        }
+        if (have) rb.role[i] = shared ? cand : kRoleSelf;
+        // compaction: representatives (and prompts on their own) / followers
+        const uint32_t ma = __ballot_sync(0xffffffffu, have && !shared), mf = __ballot_sync(0xffffffffu, shared);
+        unsigned int ba = 0, bf = 0;
+        if (lane == 0) { if (ma) ba = atomicAdd(&rb.n_hl[0], (unsigned int)__popc(ma)); if (mf) bf = atomicAdd(&rb.n_hl[1], (unsigned int)__popc(mf)); }
+        ba = __shfl_sync(0xffffffffu, ba, 0); bf = __shfl_sync(0xffffffffu, bf, 0);
+        const uint32_t below = (1u << lane) - 1u;
+        if (have && !shared) rb.hl[ba + __popc(ma & below)] = i;
+        if (shared) rb.fl[bf + __popc(mf & below)] = i;
     }
 }
 
@@ -170,12 +250,12 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
     using SM = HashSmem<BS>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned int n_hl = *rb.n_hl;                                   // slots that hash this round (kernel G)
+    const unsigned int n_hl = rb.n_hl[0];                                 // representatives this round (kernel G)
     const unsigned int total_warps = gridDim.x * (kHashThreads / 32);
     for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_hl; w += total_warps) {
-        const bool have = w * 32u + lane < n_hl;
-        const unsigned int i = have ? rb.hl[w * 32u + lane] : 0u;        // slot in the active list
-        const uint32_t p = have ? rb.act[cur][i] : 0u;
+        const unsigned int i = w * 32u + lane;                            // position in the representative list
+        const bool have = i < n_hl;
+        const uint32_t p = have ? rb.act[cur][rb.hl[i]] : 0u;
         int nb = 0;                                                      // blocks of this prompt in this round
         const uint32_t* src = nullptr;
         bool aligned = true;
@@ -277,25 +357,27 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     WalkSmem::Warp& W = sm.w[wid];
     if (threadIdx.x < 16) sm.weight[threadIdx.x] = t.weight[threadIdx.x];
     __syncthreads();
-    const unsigned int n_act = rb.n_act[cur];
+    const unsigned int n_act = rb.n_hl[0];                     // representatives this round
     const size_t kstride = (size_t)a.n_prompts;
     const bool peer = t.shard_bits != 0;
+    const PromptState* pst_prev = rb.pst[(round & 1) ^ 1];
+    PromptState* pst_cur = rb.pst[round & 1];
     const unsigned int total_warps = gridDim.x * (kProbeThreads / 32);
     for (unsigned int w = blockIdx.x * (kProbeThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
-        const unsigned int i = w * 32u + lane;
+        const unsigned int i = w * 32u + lane;                 // position in the representative list
         const bool have = i < n_act;
-        const uint32_t p = have ? rb.act[cur][i] : 0u;
-        const uint32_t meta = have ? rb.nbr[i] : 0u;
+        const unsigned int li = have ? rb.hl[i] : 0u;          // its live slot
+        const uint32_t p = have ? rb.act[cur][li] : 0u;
+        const uint32_t meta = have ? rb.nbr[li] : 0u;
         const int nb = (int)(meta & 63u);
         const bool has_more = (meta >> 8) & 1u;
         const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
-        const uint32_t rl = have ? rb.role[i] : kRoleSelf;
-        const unsigned int ks = rl == kRoleSelf ? i : rl;       // list slot whose keys this prompt reads (its own or its leader's)
+        const unsigned int ks = i;
         uint64_t lastkey = 0;
         uint32_t k = 0, alive = 0;
         uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0;      // last scored pattern
         if (round > 0 && have) {
-            const PromptState& ps = rb.pst[p];
+            const PromptState& ps = pst_prev[rb.src[p]];
             k = ps.k; alive = ps.alive;
             pv0 = ps.pat[0]; pv1 = ps.pat[1]; pv2 = ps.pat[2]; pv3 = ps.pat[3]; pv4 = ps.pat[4]; pvc = ps.pat[5];
             for (uint32_t q = 0; q < k; ++q) { W.sc[q][lane] = ps.sc[q]; W.pod[q][lane] = ps.pod[q]; W.bt[q][lane] = ps.bt[q]; }
@@ -402,12 +484,19 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             base = __shfl_sync(0xffffffffu, base, 0);
             if (more) {
                 rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
-                PromptState& ps = rb.pst[p];
+                PromptState& ps = pst_cur[p];
                 rb.hstate[p] = lastkey;                          // chain state for the next round (key of this round's last block)
+                rb.src[p] = p;
                 ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
                 ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
                 for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; ps.bt[q] = W.bt[q][lane]; }
             }
+        }
+        if (have) rb.fate[li] = more ? kFateMore : kFateDone;
+        if (have && !more) {                                   // final pods and scores, for followers of this class (kernel R)
+            PromptState& ps = pst_cur[p];
+            ps.k = (uint8_t)k;
+            for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; }
         }
         __syncwarp();
         uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
@@ -437,12 +526,70 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     }
 }
 
+// ---- kernel R: followers take their representative's outcome --------------------------------------------------
+// Lane per follower.  Representative continues: so does the follower, with the representative's chain state, and its
+// walk state stays where the representative left it (src).  Representative finished: same pods, same scores -- the warp
+// writes the follower's result from the representative's final state.
+__global__ void __launch_bounds__(256)
+resolve_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_fl = rb.n_hl[1];
+    const PromptState* pst_cur = rb.pst[round & 1];
+    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
+    for (unsigned int w = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_fl; w += total_warps) {
+        const unsigned int f = w * 32u + lane;
+        const bool have = f < n_fl;
+        uint32_t p = 0, pl = 0; uint8_t ft = 0;
+        if (have) {
+            const unsigned int li = rb.fl[f], lj = rb.role[li];
+            p = rb.act[cur][li]; pl = rb.act[cur][lj]; ft = rb.fate[lj];
+        }
+        const bool more = have && ft == kFateMore;
+        const uint32_t mm = __ballot_sync(0xffffffffu, more);
+        if (mm) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (more) {
+                rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
+                rb.src[p] = pl;
+                rb.hstate[p] = rb.hstate[pl];
+            }
+        }
+        uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
+        while (dm) {
+            const int l = __ffs(dm) - 1; dm &= dm - 1;
+            const uint32_t pp = __shfl_sync(0xffffffffu, p, l);
+            const PromptState& ps = pst_cur[__shfl_sync(0xffffffffu, pl, l)];
+            const uint32_t pk = ps.k;
+            if (a.dense) {
+                double* row = a.dense + (long long)pp * t.max_pods;
+                const uint32_t P = t.max_pods;
+                if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                    for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
+                } else {
+                    for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
+                }
+                __syncwarp();
+                if ((uint32_t)lane < pk) { const uint32_t pd = ps.pod[lane]; if (pd < P) row[pd] = ps.sc[lane]; }
+            }
+            if (a.sp_cnt) {
+                if ((uint32_t)lane < pk) { a.sp_pods[(long long)pp * kMaxEnt + lane] = ps.pod[lane]; a.sp_scores[(long long)pp * kMaxEnt + lane] = ps.sc[lane]; }
+                if (lane == 0) a.sp_cnt[pp] = (uint8_t)pk;
+            }
+            if (a.has_keys && lane == 0) a.has_keys[pp] = 1;     // followers always have a block in the round
+        }
+        __syncwarp();
+    }
+}
+
 // List setup + a 64-bit fingerprint of every prompt's first block.  The batch is then radix-sorted by fingerprint so
 // that prompts sharing a prefix sit in neighbouring lanes: their probes are the same 64-byte segments, which the
 // load unit merges within a warp and L2 serves across warps.  (Any order gives the same results; this one lets the
 // prefix sharing the system exists for -- system prompts, shared documents -- show up as memory locality.)
+struct PartSizes { unsigned int n[kMaxParts]; };
 __global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsigned long long* max_blocks, uint64_t* fp, uint32_t* idx,
-                                   unsigned int* n_act, unsigned int n_first) {
+                                   unsigned int* cnt, const PartSizes ps) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     unsigned long long nb = 0;
     if (i < a.n_prompts) {
@@ -459,7 +606,7 @@ __global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsig
     }
     nb = __reduce_max_sync(0xffffffffu, (unsigned)min(nb, 0xffffffffull));
     if ((threadIdx.x & 31) == 0 && nb) atomicMax(max_blocks, nb);
-    if (i == 0) { n_act[0] = n_first; n_act[1] = 0; n_act[2] = (unsigned int)a.n_prompts - n_first; n_act[3] = 0; }
+    if (i == 0) for (int q = 0; q < kMaxParts; ++q) { cnt[4 * q] = ps.n[q]; cnt[4 * q + 1] = 0; }      // live-list lengths per part
 }
 
 inline int rounds_init() {

@@ -97,12 +97,13 @@ struct kvidx {
     int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
-    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map;
+    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate;
+    int rounds_parts = 2;          // parts (streams) a large batch is split into
     int rounds_dedup = 1;          // chunk-level prefix sharing in the round pipeline
     int sort_prefix = 1;           // sort the batch by first-block fingerprint before the rounds
     int rounds_overlap = 1;        // run the two halves of a large batch on two streams
     int64_t rounds_overlap_min = 65536;
-    cudaStream_t aux_stream = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -202,39 +203,50 @@ int enforce_caps(kvidx* x) {
 
 struct ScoreOut { double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* sp_cnt; uint8_t* has_keys; };
 
-// Large batches: alternating hash / probe rounds (kernels_rounds.cuh).  max_blocks < 0: computed on the device.
-// The sorted batch is split into two halves that run their rounds on two streams, so the compute-bound hash kernel
-// of one half shares the SMs with the memory-bound walk kernel of the other.
+// Large batches: rounds of group / hash / walk / resolve kernels (kernels_rounds.cuh).  max_blocks < 0: computed on the
+// device.  The sorted batch is split into parts that run their rounds on separate streams, so that one part's
+// latency-bound kernels (the serial FNV chain of few representatives, the dependent probes) share the SMs with
+// another part's bandwidth-bound ones.
 int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
                         const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
                         int64_t max_blocks) {
-    CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(64));
-    CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState)));
-    CK(x->r_nbr.need((size_t)n * 4)); CK(x->r_role.need((size_t)n * 4)); CK(x->r_hl.need((size_t)n * 4));
-    const uint64_t map_slots = pow2ceil((uint64_t)std::max<int64_t>(4 * n, 1024));
-    CK(x->r_map.need(map_slots * 4 * 2));
-    const bool overlap = x->rounds_overlap && n >= x->rounds_overlap_min;
-    const int64_t nA = overlap ? ((n / 2 + 31) & ~31ll) : n, nB = n - nA;
+    CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(512));
+    CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState) * 2));
+    CK(x->r_nbr.need((size_t)n * 4)); CK(x->r_role.need((size_t)n * 4)); CK(x->r_hl.need((size_t)n * 4 * 2)); CK(x->r_src.need((size_t)n * 4));
+    CK(x->r_fate.need((size_t)n));
+    int np = 1;
+    if (x->rounds_overlap && n >= x->rounds_overlap_min) np = std::max(1, std::min(kMaxParts, x->rounds_parts));
+    int64_t psz[kMaxParts] = {0, 0, 0, 0}, poff[kMaxParts] = {0, 0, 0, 0};
+    {
+        const int64_t per = ((n + np - 1) / np + 31) & ~31ll;
+        int64_t at = 0;
+        for (int q = 0; q < np; ++q) { poff[q] = at; psz[q] = std::max<int64_t>(0, std::min(per, n - at)); at += psz[q]; }
+    }
+    const uint64_t map_slots = pow2ceil((uint64_t)std::max<int64_t>(4 * ((n + np - 1) / np), 1024));
+    CK(x->r_map.need(map_slots * 4 * np));
     unsigned int* cnt = x->r_cnt.as<unsigned int>();
-    unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(x->r_cnt.as<unsigned char>() + 16);
-    RoundBufs rb[2]{};
-    for (int hlf = 0; hlf < 2; ++hlf) {
-        const int64_t off = hlf ? nA : 0;
-        rb[hlf].act[0] = x->r_act0.as<uint32_t>() + off; rb[hlf].act[1] = x->r_act1.as<uint32_t>() + off;
-        rb[hlf].n_act = cnt + 2 * hlf;
-        rb[hlf].hstate = x->r_hstate.as<uint64_t>(); rb[hlf].pst = x->r_pst.as<PromptState>();
-        rb[hlf].keys = x->r_keys.as<uint64_t>() + off; rb[hlf].nbr = x->r_nbr.as<uint32_t>() + off;
-        rb[hlf].role = x->r_role.as<uint32_t>() + off; rb[hlf].hl = x->r_hl.as<uint32_t>() + off;
-        rb[hlf].n_hl = cnt + 8 + hlf;
-        rb[hlf].map = x->r_map.as<uint32_t>() + (hlf ? map_slots : 0); rb[hlf].map_mask = (uint32_t)(map_slots - 1);
+    unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(cnt + 32);
+    RoundBufs rb[kMaxParts]{};
+    for (int q = 0; q < np; ++q) {
+        const int64_t off = poff[q];
+        rb[q].act[0] = x->r_act0.as<uint32_t>() + off; rb[q].act[1] = x->r_act1.as<uint32_t>() + off;
+        rb[q].n_act = cnt + 4 * q;
+        rb[q].n_hl = cnt + 4 * q + 2;
+        rb[q].hstate = x->r_hstate.as<uint64_t>(); rb[q].src = x->r_src.as<uint32_t>();
+        rb[q].pst[0] = x->r_pst.as<PromptState>(); rb[q].pst[1] = x->r_pst.as<PromptState>() + n;
+        rb[q].keys = x->r_keys.as<uint64_t>() + off; rb[q].nbr = x->r_nbr.as<uint32_t>() + off;
+        rb[q].role = x->r_role.as<uint32_t>() + off; rb[q].fate = x->r_fate.as<uint8_t>() + off;
+        rb[q].hl = x->r_hl.as<uint32_t>() + off; rb[q].fl = x->r_hl.as<uint32_t>() + n + off;
+        rb[q].map = x->r_map.as<uint32_t>() + (size_t)q * map_slots; rb[q].map_mask = (uint32_t)(map_slots - 1);
     }
     ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
-    CK(cudaMemsetAsync(x->r_cnt.p, 0, 64, st));
+    CK(cudaMemsetAsync(x->r_cnt.p, 0, 512, st));
     CK(x->r_fp.need((size_t)n * 8 * 2 + (size_t)n * 4));
     uint64_t* fp_in = x->r_fp.as<uint64_t>(); uint64_t* fp_out = fp_in + n;
     uint32_t* idx_in = reinterpret_cast<uint32_t*>(fp_out + n);
-    rounds_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, x->tv.block_size, d_maxb, fp_in, x->sort_prefix ? idx_in : rb[0].act[0], cnt,
-                                                                    (unsigned int)nA);
+    PartSizes ps{};
+    for (int q = 0; q < kMaxParts; ++q) ps.n[q] = (unsigned int)psz[q];
+    rounds_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, x->tv.block_size, d_maxb, fp_in, x->sort_prefix ? idx_in : rb[0].act[0], cnt, ps);
     x->launches += 1;
     CK(cudaGetLastError());
     if (x->sort_prefix) {
@@ -252,30 +264,34 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
     }
     int64_t rounds = (max_blocks + kRoundBlocks - 1) / kRoundBlocks;
     if (rounds < 1) rounds = 1;                       // round 0 also retires the prompts that have no full block
-    cudaStream_t strm[2] = {st, x->aux_stream};
-    const int nh = nB > 0 ? 2 : 1;
-    if (nh == 2) { CK(cudaEventRecord(x->ev_fork, st)); CK(cudaStreamWaitEvent(x->aux_stream, x->ev_fork, 0)); }
-    const int per_sm_h = nh == 2 ? 2 : 4, per_sm_p = nh == 2 ? 2 : 4;
+    cudaStream_t strm[kMaxParts] = {st, x->aux_stream[0], x->aux_stream[1], x->aux_stream[2]};
+    if (np > 1) {
+        CK(cudaEventRecord(x->ev_fork, st));
+        for (int q = 1; q < np; ++q) CK(cudaStreamWaitEvent(strm[q], x->ev_fork, 0));
+    }
+    const int per_sm = np == 1 ? 4 : 2;
     for (int64_t r = 0; r < rounds; ++r) {
         const int cur = (int)(r & 1);
-        for (int hlf = 0; hlf < nh; ++hlf) {
-            const int64_t m = hlf ? nB : nA;
-            CK(cudaMemsetAsync(rb[hlf].map, 0xff, map_slots * 4, strm[hlf]));
-            CK(cudaMemsetAsync(rb[hlf].n_hl, 0, 4, strm[hlf]));
-            const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads / 32 - 1) / (kGroupThreads / 32), (int64_t)x->sm_count * 8);
-            group_round_kernel<16><<<ggrid, kGroupThreads, 0, strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r, x->rounds_dedup);
-            const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * per_sm_h);
-            hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+        for (int q = 0; q < np; ++q) {
+            const int64_t m = psz[q];
+            if (m <= 0) continue;
+            CK(cudaMemsetAsync(rb[q].map, 0xff, map_slots * 4, strm[q]));
+            CK(cudaMemsetAsync(rb[q].n_hl, 0, 8, strm[q]));
+            const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads - 1) / kGroupThreads, (int64_t)x->sm_count * (np == 1 ? 8 : 4));
+            group_round_kernel<16><<<ggrid, kGroupThreads, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
+            const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * per_sm);
+            hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
+            const unsigned pgrid = (unsigned)std::min<int64_t>((m + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * per_sm);
+            probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
+            if (x->rounds_dedup) {
+                const unsigned rgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * 2);
+                resolve_round_kernel<<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
+            }
+            x->launches += x->rounds_dedup ? 4 : 3;
         }
-        for (int hlf = 0; hlf < nh; ++hlf) {
-            const int64_t m = hlf ? nB : nA;
-            const unsigned pgrid = (unsigned)std::min<int64_t>((m + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * per_sm_p);
-            probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
-        }
-        x->launches += 3 * nh;
     }
     CK(cudaGetLastError());
-    if (nh == 2) { CK(cudaEventRecord(x->ev_join, x->aux_stream)); CK(cudaStreamWaitEvent(st, x->ev_join, 0)); }
+    for (int q = 1; q < np; ++q) { CK(cudaEventRecord(x->ev_join[q - 1], strm[q])); CK(cudaStreamWaitEvent(st, x->ev_join[q - 1], 0)); }
     return 0;
 }
 
@@ -516,9 +532,11 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     CK(cudaStreamCreateWithFlags(&x->own_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&x->aux_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < 3; ++q) {
+        CK(cudaStreamCreateWithFlags(&x->aux_stream[q], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&x->ev_join[q], cudaEventDisableTiming));
+    }
     CK(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&x->ev_join, cudaEventDisableTiming));
     x->stream = x->own_stream;
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
@@ -560,6 +578,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
     if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
     if (rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
@@ -580,7 +599,7 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_done[i]) cudaEventDestroy(x->ev_done[i]);
         if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]);
     }
-    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release(); x->r_role.release(); x->r_hl.release(); x->r_map.release();
+    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release(); x->r_role.release(); x->r_hl.release(); x->r_map.release(); x->r_src.release(); x->r_fate.release();
     x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
     if (x->tv.req) cudaFree(x->tv.req);
     if (x->tv.eng) cudaFree(x->tv.eng);
@@ -590,9 +609,11 @@ void kvidx_destroy(kvidx_t* x) {
     if (x->own_stream) cudaStreamDestroy(x->own_stream);
     if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
     if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
-    if (x->aux_stream) cudaStreamDestroy(x->aux_stream);
+    for (int q = 0; q < 3; ++q) {
+        if (x->aux_stream[q]) cudaStreamDestroy(x->aux_stream[q]);
+        if (x->ev_join[q]) cudaEventDestroy(x->ev_join[q]);
+    }
     if (x->ev_fork) cudaEventDestroy(x->ev_fork);
-    if (x->ev_join) cudaEventDestroy(x->ev_join);
     delete x;
 }
 

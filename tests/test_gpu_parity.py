@@ -273,6 +273,10 @@ def _select_path(monkeypatch, path):
     elif path == "rounds2":
         monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
         monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP_MIN", "64")
+    elif path == "rounds4":
+        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
+        monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP_MIN", "64")
+        monkeypatch.setenv("KVIDX_ROUNDS_PARTS", "4")
     elif path == "rounds-nosort":
         monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
         monkeypatch.setenv("KVIDX_SORT_PREFIX", "0")
@@ -284,7 +288,7 @@ def _select_path(monkeypatch, path):
         monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP", "0")
 
 
-PATHS = ["v1", "fused", "rounds", "rounds2", "rounds-nosort", "rounds-nodedup"]
+PATHS = ["v1", "fused", "rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-nodedup"]
 
 
 @pytest.mark.parametrize("kernel", PATHS)
@@ -308,7 +312,7 @@ def test_synth_config2_shape_vs_oracle_and_closed_form(kernel, monkeypatch):
     assert np.array_equal(s1, wl.expected_scores(doc, m))
 
 
-@pytest.mark.parametrize("kernel", ["fused", "rounds", "rounds2", "rounds-nosort"])
+@pytest.mark.parametrize("kernel", ["fused", "rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-nodedup"])
 def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
     """Lane refill / round lists, unaligned prompt starts (per-lane staging fallback), empty and sub-block
     prompts, pod filters, against the oracle."""
@@ -342,7 +346,7 @@ def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
         assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
 
 
-@pytest.mark.parametrize("kernel", ["rounds", "rounds2", "rounds-nosort"])
+@pytest.mark.parametrize("kernel", ["rounds", "rounds2", "rounds4", "rounds-nosort"])
 def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
     """The round pipeline lets a prompt reuse another prompt's keys when chain state and the next 32-block chunk are
     identical.  Few documents, thousands of prompts: exact duplicates, prefixes of every length (so the shared chunk is
