@@ -42,12 +42,13 @@ struct __align__(8) PromptState {        // walk state carried between rounds (o
     uint8_t pad2[2];
 };
 
-constexpr int kMaxParts = 4;              // the sorted batch runs as up to this many independent parts on their own streams
+constexpr int kMaxParts = 8;              // the sorted batch runs as up to this many independent parts on their own streams
 
 struct RoundBufs {
     uint32_t* act[2];                    // live prompt lists (ping-pong)
     unsigned int* n_act;                 // [2] list lengths
     uint64_t* hstate;                    // per prompt: chain hash after the last block of the previous round
+    uint32_t* pos;                       // per prompt: first block of its next chunk (32 x round unless it walked part of a chunk alone)
     uint32_t* src;                       // per prompt: the prompt whose PromptState (previous round's buffer) is this prompt's
                                          // walk state -- itself, or the representative of the class it was in
     PromptState* pst[2];                 // per prompt, by round parity (round r reads [r&1 ^ 1], writes [r&1])
@@ -61,7 +62,28 @@ struct RoundBufs {
     uint8_t* fate;                       // [n_act] written for representatives by kernel P: kFateMore / kFateDone
     uint32_t* hl;                        // [n_act] representative list (live slots), compacted
     uint32_t* fl;                        // [n_act] follower list (live slots), compacted
-    unsigned int* n_hl;                  // n_hl[0] = representatives, n_hl[1] = followers (zeroed before every round)
+    uint32_t* dl;                        // [n_act] partial-follower list (live slots), compacted
+    unsigned int* n_hl;                  // [0] representatives, [1] followers, [2] partial followers (zeroed before every round)
+    // partial followers: a prompt alone in its class whose chunk starts like a neighbouring class's chunk (it leaves a
+    // popular prefix inside this chunk) shares the first dmin blocks with that class -- keys and walk -- and continues on
+    // its own from there (detach_round_kernel)
+    uint8_t* nfol;                       // [n_act] live slot has followers (it must stay a representative); zeroed per round
+    uint8_t* need_snap;                  // [n_act] representative must record its walk state after every block; zeroed per round
+    uint32_t* anch;                      // [n_act] live slot of the representative it could share a chunk prefix with
+    uint8_t* dmin;                       // [n_act] ... and the number of leading blocks it shares (0: none)
+    uint32_t* apos;                      // [n_act] live slot -> position in the representative list
+    uint32_t* lslot;                     // per prompt: its slot in the current live list (written when the list is built)
+    uint4* rec;                          // [n_hl] per representative {prompt, live slot, nbr word, src}: one load instead of a chain
+    uint4* drec;                         // [n_dl] per partial follower {prompt, representative's live slot, shared blocks << 16 | nbr word, representative's prompt}
+    uint32_t* grp;                       // [n_act] by live slot of last round's representative R: a class of this round whose members
+                                         // had R's state (kRoleSelf: none); cleared with the map
+    uint8_t* nwalk;                      // [n_hl] blocks of the round after which the representative's walk was still alive
+    // walk snapshots, one per RUN of blocks with the same slot pattern: state after the run's first block; the state after a
+    // later block of the run is that plus (distance) in-order additions of the same per-pod addend
+    uint8_t* snap_run;                   // [n_hl][32] first block of the run block j belongs to
+    uint16_t* snap_alive;                // [n_hl][32] alive mask after block j (stored at run starts)
+    uint8_t* snap_bt;                    // [n_hl][32][kMaxEnt] tier that gives pod q its addend (0xff: 0.0) (at run starts)
+    double* snap_sc;                     // [n_hl][32][kMaxEnt] scores after block j (at run starts)
     uint32_t* map;                       // class election: bucket -> live slot (kRoleSelf = empty), cleared before every round
     uint32_t map_mask;
 };
@@ -94,10 +116,15 @@ __device__ __forceinline__ void chunk_load(const uint32_t* sp, int nw, int lane,
     }
 }
 
+constexpr int kGroupRing = 4;            // chunks of shared memory per warp: one being compared, its predecessor, two in flight
+struct GroupSmem { uint4 ring[kGroupThreads / 32][kGroupRing][4][32]; };     // 64 KB
+
 template <int BS>
-__global__ void __launch_bounds__(kGroupThreads)
+__global__ void __launch_bounds__(kGroupThreads, 3)
 group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int dedup) {
     static_assert(BS == 16 && kRoundBlocks == 32, "a chunk is 4 x 32 lanes x 16 bytes");
+    extern __shared__ __align__(128) unsigned char smem_raw_g[];
+    uint4 (*ring)[4][32] = reinterpret_cast<GroupSmem*>(smem_raw_g)->ring[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned int n_act = rb.n_act[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
@@ -109,9 +136,10 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         int nb = 0; bool more = false;
         uint64_t hprev = t.init_hash;
         const uint32_t* tp = a.tok;
-        int64_t first = (int64_t)round * kRoundBlocks;
+        int64_t first = 0;
         if (have) {
             p = rb.act[cur][i];
+            if (round > 0) first = rb.pos[p];
             const int64_t b = a.tok_off[p] - a.tok_base, e = a.tok_off[p + 1] - a.tok_base;
             const int64_t nblk = (e - b) / BS;
             nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
@@ -126,42 +154,79 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         // but the tokens lane-parallel here; the tokens as the chunks stream by below.
         uint64_t fsum = 0;
         if (cls && round == 0 && a.filter) { const uint64_t* fr = a.filter + (int64_t)p * t.filter_words; for (uint32_t x = 0; x < t.filter_words; ++x) fsum = (fsum ^ fr[x]) * 0x9E3779B97F4A7C15ull; }
-        bool eqm;
+        bool eqm, eqf;                               // compatible with the predecessor for sharing a chunk prefix / a whole chunk
+        const int nb_up = __shfl_up_sync(0xffffffffu, nb, 1);
         {
-            const int nb_u = __shfl_up_sync(0xffffffffu, nb, 1); const int more_u = __shfl_up_sync(0xffffffffu, (int)more, 1);
+            const int more_u = __shfl_up_sync(0xffffffffu, (int)more, 1);
             const uint32_t mdl_u = __shfl_up_sync(0xffffffffu, mdl, 1), src_u = __shfl_up_sync(0xffffffffu, srcp, 1);
             const uint64_t h_u = __shfl_up_sync(0xffffffffu, hprev, 1), f_u = __shfl_up_sync(0xffffffffu, fsum, 1);
             const int cls_u = __shfl_up_sync(0xffffffffu, (int)cls, 1);
-            eqm = cls && lane > 0 && cls_u && nb_u == nb && more_u == (int)more && mdl_u == mdl && src_u == srcp && h_u == hprev && f_u == fsum;
+            eqm = cls && lane > 0 && cls_u && mdl_u == mdl && src_u == srcp && h_u == hprev && f_u == fsum;
             if (eqm && round == 0 && a.filter) {       // equal filter fingerprints: compare the rows themselves
                 const uint32_t pu = rb.act[cur][i - 1];
                 const uint64_t* fa = a.filter + (int64_t)p * t.filter_words; const uint64_t* fb = a.filter + (int64_t)pu * t.filter_words;
                 for (uint32_t x = 0; x < t.filter_words; ++x) eqm = eqm && fa[x] == fb[x];
             }
+            eqf = eqm && nb_up == nb && more_u == (int)more;
         }
-        // chunks, one prompt at a time, the next one in flight while this one is compared with the previous one (still in
-        // registers) and -- only if it differs -- folded into a fingerprint for the election
+        // chunks, one prompt at a time: each is compared with its predecessor's (still in the ring) and -- only if it
+        // differs -- folded into a fingerprint for the election
         uint32_t f0 = 0, f1 = 0;
         bool eqprev = false;                         // same class as the previous list entry
+        int dprev = 0;                               // leading blocks of the chunk equal to the previous list entry's
         uint32_t todo = __ballot_sync(0xffffffffu, cls);
-        const uint32_t eqm_mask = __ballot_sync(0xffffffffu, eqm);
-        uint4 v[4], vn[4], vp[4];
+        const uint32_t eqm_mask = __ballot_sync(0xffffffffu, eqm), eqf_mask = __ballot_sync(0xffffffffu, eqf);
+        // chunk q of the list lands in ring slot (its ordinal % kGroupRing) through cp.async; two chunks stay in flight
+        auto issue = [&](int slot, int qi) {
+            if (qi >= 0) {
+                const uint32_t* sp = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, qi));
+                const int nw = __shfl_sync(0xffffffffu, nb, qi) * BS;
+                const bool al = (reinterpret_cast<uintptr_t>(sp) & 15u) == 0;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) vp[c] = make_uint4(0, 0, 0, 0);
-        int q = todo ? __ffs(todo) - 1 : -1, qprev = -2;
-        if (q >= 0) chunk_load(reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, q)),
-                               __shfl_sync(0xffffffffu, nb, q) * BS, lane, v);
-        while (q >= 0) {
+                for (int c = 0; c < 4; ++c) {
+                    const int w0 = (c * 32 + lane) * 4;
+                    uint4* dst = &ring[slot][c][lane];
+                    if (w0 < nw) {
+                        if (al) cp_async_16(smem_addr(dst), sp + w0);
+                        else *dst = make_uint4(__ldg(sp + w0), __ldg(sp + w0 + 1), __ldg(sp + w0 + 2), __ldg(sp + w0 + 3));
+                    } else *dst = make_uint4(0, 0, 0, 0);
+                }
+            }
+            cp_async_commit();
+        };
+        constexpr int PD = kGroupRing - 2;
+        uint32_t pend = todo;
+        int issued = 0;
+#pragma unroll
+        for (int u = 0; u < PD; ++u) {
+            const int qi = pend ? __ffs(pend) - 1 : -1;
+            pend &= pend - 1;
+            issue(issued % kGroupRing, qi); ++issued;
+        }
+        int qprev = -2, ord = 0;
+        while (todo) {
+            const int q = __ffs(todo) - 1;
             todo &= todo - 1;
-            const int qn = todo ? __ffs(todo) - 1 : -1;
-            if (qn >= 0) chunk_load(reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, qn)),
-                                    __shfl_sync(0xffffffffu, nb, qn) * BS, lane, vn);
+            {
+                const int qi = pend ? __ffs(pend) - 1 : -1;
+                pend &= pend - 1;
+                issue(issued % kGroupRing, qi); ++issued;
+            }
+            cp_async_wait<PD>();
+            uint4 v[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[c] = ring[ord % kGroupRing][c][lane];
             bool same = false;
             if (qprev == q - 1 && ((eqm_mask >> q) & 1u)) {          // warp-uniform
-                uint32_t d = 0;
+                int fb = 32;                                          // first block in which this lane's pieces differ
 #pragma unroll
-                for (int c = 0; c < 4; ++c) d |= (v[c].x ^ vp[c].x) | (v[c].y ^ vp[c].y) | (v[c].z ^ vp[c].z) | (v[c].w ^ vp[c].w);
-                same = __all_sync(0xffffffffu, d == 0u);
+                for (int c = 3; c >= 0; --c) {
+                    const uint4 u = ring[(ord + kGroupRing - 1) % kGroupRing][c][lane];
+                    if (((v[c].x ^ u.x) | (v[c].y ^ u.y) | (v[c].z ^ u.z) | (v[c].w ^ u.w)) != 0u) fb = c * 8 + (lane >> 2);
+                }
+                fb = __reduce_min_sync(0xffffffffu, fb);
+                same = fb == 32 && ((eqf_mask >> q) & 1u);
+                if (lane == q) dprev = min(fb, min(nb, nb_up));
             }
             if (same) { if (lane == q) eqprev = true; }
             else {
@@ -177,10 +242,9 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 a1 = __reduce_xor_sync(0xffffffffu, a1);
                 if (lane == q) { f0 = a0; f1 = a1; }
             }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { vp[c] = v[c]; v[c] = vn[c]; }
-            qprev = q; q = qn;
+            qprev = q; ++ord;
         }
+        cp_async_wait<0>();
         // election among the prompts that differ from their predecessor
         uint32_t cand = kRoleSelf;
         if (cls && !eqprev) {
@@ -212,6 +276,7 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             const uint32_t* s1 = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, l));
             const uint32_t* s2 = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)lp, l));
             const int nw = __shfl_sync(0xffffffffu, nb, l) * BS;
+            uint4 v[4], vn[4];
             chunk_load(s1, nw, lane, v);
             chunk_load(s2, nw, lane, vn);
             uint32_t d = 0;
@@ -229,15 +294,119 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             const unsigned int i_h = __shfl_sync(0xffffffffu, i, hd);
             if (eqprev) { shared = true; cand = shared_h ? cand_h : i_h; }
         }
-        if (have) rb.role[i] = shared ? cand : kRoleSelf;
-        // compaction: representatives (and prompts on their own) / followers
-        const uint32_t ma = __ballot_sync(0xffffffffu, have && !shared), mf = __ballot_sync(0xffffffffu, shared);
-        unsigned int ba = 0, bf = 0;
-        if (lane == 0) { if (ma) ba = atomicAdd(&rb.n_hl[0], (unsigned int)__popc(ma)); if (mf) bf = atomicAdd(&rb.n_hl[1], (unsigned int)__popc(mf)); }
-        ba = __shfl_sync(0xffffffffu, ba, 0); bf = __shfl_sync(0xffffffffu, bf, 0);
+        if (have) { rb.role[i] = shared ? cand : kRoleSelf; if (shared) rb.nfol[cand] = 1; }
+        // Every member of a class tells the prompts that shared its state last round (same src) where the class lives:
+        // kernel G2 compares the ones that stayed alone with this class's chunk.
+        if (shared && round > 0) rb.grp[rb.lslot[srcp]] = cand;
+        // A prompt that stayed alone may also start like a neighbouring class: walk the list (<= 8 entries each way) to the nearest
+        // member of a class; the chunk prefix shared with it is at least the minimum of the pairwise shared prefixes on
+        // the way.  kernel G2 turns either into a partial-follower role if nobody follows the prompt itself.
+        {
+            int mb = 32, mf = 32, db = 0, df = 0;
+            uint32_t rb_ = kRoleSelf, rf_ = kRoleSelf;
+#pragma unroll
+            for (int sft = 1; sft <= 8; ++sft) {
+                const int sb = max(lane - sft, 0), sf = min(lane + sft, 31);
+                const int dp_b = __shfl_sync(0xffffffffu, dprev, min(sb + 1, 31));      // dprev[lane - sft + 1]
+                const int dp_f = __shfl_sync(0xffffffffu, dprev, sf);                   // dprev[lane + sft]
+                const int an_b = __shfl_sync(0xffffffffu, (int)shared, sb), an_f = __shfl_sync(0xffffffffu, (int)shared, sf);
+                const uint32_t cb = __shfl_sync(0xffffffffu, cand, sb), cf = __shfl_sync(0xffffffffu, cand, sf);
+                if (lane - sft >= 0 && rb_ == kRoleSelf && mb > 0) { mb = min(mb, dp_b); if (an_b && mb > 0) { rb_ = cb; db = mb; } }
+                if (lane + sft <= 31 && rf_ == kRoleSelf && mf > 0) { mf = min(mf, dp_f); if (an_f && mf > 0) { rf_ = cf; df = mf; } }
+            }
+            if (have) {
+                const bool useb = db >= df;
+                rb.anch[i] = useb ? rb_ : rf_;
+                rb.dmin[i] = (uint8_t)((cls && !shared) ? (useb ? db : df) : 0);
+            }
+        }
+    }
+}
+
+// ---- kernel G2: partial followers, and the three lists -----------------------------------------------------------
+// A prompt that ended up alone in its class and that nobody follows looks for a class whose chunk starts like its own:
+// the class that prompts with its state joined this round (grp), else last round's representative itself, else -- round
+// 0, or nothing better -- the class of a list neighbour (kernel G's hint).  The shared prefix is then measured exactly,
+// token by token against that class's chunk (warp-wide), so that the prompt detaches at the right block.
+template <int BS>
+__global__ void __launch_bounds__(256)
+group_lists_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int partial) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_act = rb.n_act[cur];
+    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
+    for (unsigned int w = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_act; w += total_warps) {
+        const unsigned int i = w * 32u + lane;
+        const bool have = i < n_act;
+        int kind = -1;                               // 0 representative / alone, 1 follower, 2 partial follower
+        uint32_t target = kRoleSelf;
+        const uint32_t* tp = a.tok; const uint32_t* rp = a.tok;
+        int nbc = 0;                                 // blocks both chunks have
+        if (have) {
+            kind = rb.role[i] == kRoleSelf ? 0 : 1;
+            const int nb = (int)(rb.nbr[i] & 63u);
+            if (kind == 0 && partial && nb > 0 && !rb.nfol[i]) {
+                const uint32_t p = rb.act[cur][i];
+                // (Last round's representatives never become partial followers: the prompts that shared their state may be
+                //  attaching to them right now.)
+                bool allow = true;
+                if (round > 0) {
+                    const uint32_t srcp = rb.src[p];
+                    allow = srcp != p;
+                    if (allow) { const uint32_t rs = rb.lslot[srcp]; const uint32_t g = rb.grp[rs]; target = g != kRoleSelf ? g : rs; }
+                }
+                if (allow && target == kRoleSelf && rb.dmin[i] > 0) target = rb.anch[i];
+                if (target != kRoleSelf && rb.role[target] != kRoleSelf) target = rb.role[target];   // someone with the same chunk represents it
+                if (target == i) target = kRoleSelf;
+                if (target != kRoleSelf) {
+                    const uint32_t pl = rb.act[cur][target];
+                    const int64_t first = round > 0 ? (int64_t)rb.pos[p] : 0;      // the class's too: same state
+                    const int64_t b = a.tok_off[p] - a.tok_base;
+                    const int64_t bl = a.tok_off[pl] - a.tok_base, el = a.tok_off[pl + 1] - a.tok_base;
+                    nbc = min(nb, (int)max((int64_t)0, min((int64_t)kRoundBlocks, (el - bl) / BS - first)));
+                    tp = a.tok + b + first * BS; rp = a.tok + bl + first * BS;
+                    // same walk state, model and filter as the class?  (grp / src: by construction; the neighbour hint: checked by kernel G)
+                    if (round > 0 && !(rb.src[pl] == rb.src[p] && rb.hstate[pl] == rb.hstate[p])) nbc = 0;
+                }
+            }
+        }
+        int dshare = 0;
+        uint32_t wm = __ballot_sync(0xffffffffu, nbc > 0);
+        while (wm) {
+            const int l = __ffs(wm) - 1; wm &= wm - 1;
+            const uint32_t* s1 = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, l));
+            const uint32_t* s2 = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)rp, l));
+            const int nw = __shfl_sync(0xffffffffu, nbc, l) * BS;
+            uint4 v[4], vn[4];
+            chunk_load(s1, nw, lane, v);
+            chunk_load(s2, nw, lane, vn);
+            int fb = 32;
+#pragma unroll
+            for (int c = 3; c >= 0; --c)
+                if (((v[c].x ^ vn[c].x) | (v[c].y ^ vn[c].y) | (v[c].z ^ vn[c].z) | (v[c].w ^ vn[c].w)) != 0u) fb = c * 8 + (lane >> 2);
+            fb = __reduce_min_sync(0xffffffffu, fb);
+            if (lane == l) dshare = min(fb, nw / BS);
+        }
+        if (dshare > 0) { kind = 2; rb.anch[i] = target; rb.dmin[i] = (uint8_t)dshare; rb.need_snap[target] = 1; }
+        const uint32_t m0 = __ballot_sync(0xffffffffu, kind == 0), m1 = __ballot_sync(0xffffffffu, kind == 1), m2 = __ballot_sync(0xffffffffu, kind == 2);
+        unsigned int b0 = 0, b1 = 0, b2 = 0;
+        if (lane == 0) {
+            if (m0) b0 = atomicAdd(&rb.n_hl[0], (unsigned int)__popc(m0));
+            if (m1) b1 = atomicAdd(&rb.n_hl[1], (unsigned int)__popc(m1));
+            if (m2) b2 = atomicAdd(&rb.n_hl[2], (unsigned int)__popc(m2));
+        }
+        b0 = __shfl_sync(0xffffffffu, b0, 0); b1 = __shfl_sync(0xffffffffu, b1, 0); b2 = __shfl_sync(0xffffffffu, b2, 0);
         const uint32_t below = (1u << lane) - 1u;
-        if (have && !shared) rb.hl[ba + __popc(ma & below)] = i;
-        if (shared) rb.fl[bf + __popc(mf & below)] = i;
+        if (kind == 0) {
+            const unsigned int ap = b0 + __popc(m0 & below);
+            const uint32_t p = rb.act[cur][i];
+            rb.hl[ap] = i; rb.apos[i] = ap;
+            rb.rec[ap] = make_uint4(p, i, rb.nbr[i], round > 0 ? rb.src[p] : p);
+        } else if (kind == 1) rb.fl[b1 + __popc(m1 & below)] = i;
+        else if (kind == 2) {
+            const unsigned int dp = b2 + __popc(m2 & below);
+            rb.dl[dp] = i;
+            rb.drec[dp] = make_uint4(rb.act[cur][i], target, ((uint32_t)dshare << 16) | rb.nbr[i], rb.act[cur][target]);
+        }
     }
 }
 
@@ -263,7 +432,7 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
         if (have) {
             const int64_t b = a.tok_off[p] - a.tok_base, e = a.tok_off[p + 1] - a.tok_base;
             const int64_t nblk = (e - b) / BS;
-            const int64_t first = (int64_t)round * kRoundBlocks;
+            const int64_t first = round > 0 ? (int64_t)rb.pos[p] : 0;
             nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
             src = a.tok + b + first * BS;
             aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
@@ -373,6 +542,8 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         const bool has_more = (meta >> 8) & 1u;
         const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
         const unsigned int ks = i;
+        const bool snapf = have && rb.need_snap[li];           // partial followers will pick up this walk mid-chunk
+        uint32_t nwalk = 0;
         uint64_t lastkey = 0;
         uint32_t k = 0, alive = 0;
         uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0;      // last scored pattern
@@ -471,6 +642,15 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     }
                     pv0 = A.z; pv1 = A.w; pv2 = B.x; pv3 = B.y; pv4 = B.z; pvc = cnt;
                     if (!alive) done = true;
+                    else {
+                        nwalk = (uint32_t)j + 1u;
+                        if (snapf) {                        // (this kernel snapshots every block: each is its own run)
+                            rb.snap_alive[(size_t)i * kRoundBlocks + j] = (uint16_t)alive;
+                            rb.snap_run[(size_t)i * kRoundBlocks + j] = (uint8_t)j;
+                            double* sd = rb.snap_sc + ((size_t)i * kRoundBlocks + j) * kMaxEnt;
+                            for (uint32_t q = 0; q < k; ++q) sd[q] = W.sc[q][lane];
+                        }
+                    }
                 }
             }
             key = nkey; slot = nslot; base = nbase; A0 = nA0; B0 = nB0; A1 = nA1; B1 = nB1;
@@ -483,17 +663,17 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (more) {
-                rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
+                { const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u)); rb.act[cur ^ 1][ns] = p; rb.lslot[p] = ns; }
                 PromptState& ps = pst_cur[p];
                 rb.hstate[p] = lastkey;                          // chain state for the next round (key of this round's last block)
-                rb.src[p] = p;
+                rb.src[p] = p; rb.pos[p] = (round > 0 ? rb.pos[p] : 0u) + (uint32_t)nb;
                 ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
                 ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
                 for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; ps.bt[q] = W.bt[q][lane]; }
             }
         }
-        if (have) rb.fate[li] = more ? kFateMore : kFateDone;
-        if (have && !more) {                                   // final pods and scores, for followers of this class (kernel R)
+        if (have) { rb.fate[li] = more ? kFateMore : kFateDone; rb.nwalk[i] = (uint8_t)nwalk; }
+        if (have && !more) {                                   // final pods and scores, for followers of this class (kernels R, D)
             PromptState& ps = pst_cur[p];
             ps.k = (uint8_t)k;
             for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; }
@@ -526,13 +706,200 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     }
 }
 
+// ---- kernel P, warp per representative ------------------------------------------------------------------------
+// With prefix classes the representatives of a round are few (one per distinct prefix), so the lane-per-prompt walk
+// above -- 32 dependent iterations of a few hundred divergent instructions -- leaves the machine idle: its time is a
+// latency chain that does not shrink with the list.  Here a warp takes one representative: the 32 lanes probe the
+// round's 32 keys at once (one DRAM latency for the whole chunk), a ballot finds the first miss, and the blocks before
+// it are scored in order with lane q owning pod q of the first block (<= 10 pods), the block's entries broadcast by
+// shuffle.  Same arithmetic in the same order as everywhere else: max weight per pod per block, added in block order.
+__global__ void __launch_bounds__(256)
+walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_a = rb.n_hl[0];
+    const size_t kstride = (size_t)a.n_prompts;
+    const bool peer = t.shard_bits != 0;
+    const PromptState* pst_prev = rb.pst[(round & 1) ^ 1];
+    PromptState* pst_cur = rb.pst[round & 1];
+    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
+    for (unsigned int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); i < n_a; i += total_warps) {
+        const uint4 rc = __ldg(rb.rec + i);
+        uint64_t key = rb.keys[(size_t)lane * kstride + i];   // lanes >= nb read a stale key and ignore it
+        const unsigned int li = rc.y;
+        const uint32_t p = rc.x;
+        const uint32_t meta = rc.z;
+        const int nb = (int)(meta & 63u);
+        const bool has_more = (meta >> 8) & 1u;
+        const uint32_t mdl = a.model ? a.model[p] : a.model0;
+        const bool snapf = rb.need_snap[li];
+        // walk state: lane q < k owns pod q
+        uint32_t k = 0, alive = 0, mypod = 0xffffffffu, mybt = 0xffu;
+        double mysc = 0.0;
+        uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0xffffffffu;
+        if (round > 0) {
+            const PromptState& ps = pst_prev[rc.w];
+            k = ps.k; alive = ps.alive;
+            pv0 = ps.pat[0]; pv1 = ps.pat[1]; pv2 = ps.pat[2]; pv3 = ps.pat[3]; pv4 = ps.pat[4]; pvc = ps.pat[5];
+            if ((uint32_t)lane < k) { mysc = ps.sc[lane]; mypod = ps.pod[lane]; mybt = ps.bt[lane]; }
+        }
+        // probe: lane j looks up block j's key
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0, cnt = 0;
+        bool hit = false;
+        if (lane < nb) {
+            const uint64_t hm = home_of(key, mdl);
+            const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
+            uint64_t slot = hm & t.req_mask & ~1ull;
+            for (;;) {
+                uint4 A0, B0, A1, B1;
+                ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+                uint4 A = A0, B = B0;
+                hit = slot_matches(A, B, key, mdl);
+                bool stop = hit || meta_state(B.w) == kStateEmpty;
+                if (!stop) { A = A1; B = B1; hit = slot_matches(A, B, key, mdl); stop = hit || meta_state(B.w) == kStateEmpty; }
+                if (hit) { e0 = A.z; e1 = A.w; e2 = B.x; e3 = B.y; e4 = B.z; cnt = meta_count(B.w); }
+                if (stop) break;
+                slot = (slot + 2) & t.req_mask;                         // rare: displaced past the home pair
+            }
+        }
+        const uint32_t hm_ = __ballot_sync(0xffffffffu, hit);
+        const int nhit = hm_ == 0xffffffffu ? 32 : __ffs(~hm_) - 1;   // consecutive hits from block 0 (lanes >= nb never hit)
+        uint32_t nwalk = 0;
+        bool done = nb == 0;
+        // blocks whose slot holds the same pods and tiers as the block before: every live pod gets the same addend again,
+        // so a run of them is a run of in-order additions (most documents live on the same pods block after block)
+        uint32_t samemask;
+        {
+            const uint32_t u0 = __shfl_up_sync(0xffffffffu, e0, 1), u1 = __shfl_up_sync(0xffffffffu, e1, 1), u2 = __shfl_up_sync(0xffffffffu, e2, 1),
+                           u3 = __shfl_up_sync(0xffffffffu, e3, 1), u4 = __shfl_up_sync(0xffffffffu, e4, 1), uc = __shfl_up_sync(0xffffffffu, cnt, 1);
+            bool sm_ = lane > 0 ? (((u0 ^ e0) | (u1 ^ e1) | (u2 ^ e2) | (u3 ^ e3) | (u4 ^ e4) | (uc ^ cnt)) == 0u)
+                                : (round > 0 && ((pv0 ^ e0) | (pv1 ^ e1) | (pv2 ^ e2) | (pv3 ^ e3) | (pv4 ^ e4) | (pvc ^ cnt)) == 0u);
+            samemask = __ballot_sync(0xffffffffu, sm_ && lane < nhit);
+        }
+        int j = 0;
+        while (j < nhit && !done) {
+            if ((samemask >> j) & 1u) {
+                const uint32_t rest = ~(samemask >> j);
+                const int run = min(rest ? __ffs(rest) - 1 : 32, nhit - j);           // >= 1
+                const bool mine = (alive >> lane) & 1u;
+                const double add = mybt == 0xffu ? 0.0 : t.weight[mybt & 15u];
+                int u = 0;
+                if (j == 0) {                                  // the chunk opens inside a run: its first block is the snapshot
+                    if (mine) mysc = __dadd_rn(mysc, add);
+                    if (snapf) {
+                        if ((uint32_t)lane < k) { rb.snap_sc[(size_t)i * kRoundBlocks * kMaxEnt + lane] = mysc; rb.snap_bt[(size_t)i * kRoundBlocks * kMaxEnt + lane] = (uint8_t)mybt; }
+                        if (lane == 0) rb.snap_alive[(size_t)i * kRoundBlocks] = (uint16_t)alive;
+                    }
+                    u = 1;
+                }
+                if (mine) for (; u < run; ++u) mysc = __dadd_rn(mysc, add);
+                j += run;
+                nwalk = (uint32_t)j;
+                continue;
+            }
+            const uint32_t w0 = __shfl_sync(0xffffffffu, e0, j), w1 = __shfl_sync(0xffffffffu, e1, j), w2 = __shfl_sync(0xffffffffu, e2, j),
+                           w3 = __shfl_sync(0xffffffffu, e3, j), w4 = __shfl_sync(0xffffffffu, e4, j), c = __shfl_sync(0xffffffffu, cnt, j);
+            const bool first_block = round == 0 && j == 0;
+            if (first_block) {
+                // activePods := pods of block 0 (after the filter), in entry order; score = max weight   (kvblock_scorer.go:118-128)
+                const uint64_t* frow = filter_row(a.filter, p, t.filter_words);
+                k = 0;
+                for (uint32_t e = 0; e < c; ++e) {
+                    const uint32_t pt = ent_of(w0, w1, w2, w3, w4, (int)e), pd = pt >> 4;
+                    if (frow && !filter_has(frow, pd)) continue;
+                    const double wt = t.weight[pt & 15u];
+                    const uint32_t own = __ballot_sync(0xffffffffu, (uint32_t)lane < k && mypod == pd);
+                    const int q = own ? __ffs(own) - 1 : (int)k;
+                    if (!own) { if (lane == q) { mypod = pd; mysc = 0.0; mybt = 0xffu; } ++k; }
+                    if (lane == q && wt > mysc) { mysc = wt; mybt = pt & 15u; }
+                }
+                alive = (1u << k) - 1u;
+            } else {
+                // activePods &= pods(block); score[p] += max weight, in block order   (kvblock_scorer.go:130-147)
+                bool present = false; double mx = 0.0; uint32_t bt = 0xffu;
+                if ((alive >> lane) & 1u) {
+                    for (uint32_t e = 0; e < c; ++e) {
+                        const uint32_t pt = ent_of(w0, w1, w2, w3, w4, (int)e);
+                        if ((pt >> 4) == mypod) { present = true; const double wt = t.weight[pt & 15u]; if (wt > mx) { mx = wt; bt = pt & 15u; } }
+                    }
+                    if (present) { mysc = __dadd_rn(mysc, mx); mybt = bt; }
+                }
+                alive = __ballot_sync(0xffffffffu, present);
+            }
+            if (!alive) done = true;
+            else {
+                nwalk = (uint32_t)j + 1u;
+                if (snapf) {
+                    if ((uint32_t)lane < k) { rb.snap_sc[((size_t)i * kRoundBlocks + j) * kMaxEnt + lane] = mysc; rb.snap_bt[((size_t)i * kRoundBlocks + j) * kMaxEnt + lane] = (uint8_t)mybt; }
+                    if (lane == 0) rb.snap_alive[(size_t)i * kRoundBlocks + j] = (uint16_t)alive;
+                }
+            }
+            ++j;
+        }
+        if (snapf) {                                           // block -> first block of its run
+            const uint32_t starts = ~samemask & ((2u << lane) - 1u);
+            rb.snap_run[(size_t)i * kRoundBlocks + lane] = (uint8_t)(starts ? 31 - __clz(starts) : 0);
+        }
+        // pattern of the last scored block, for the next round's first comparison
+        if (j > 0) {
+            const int lj = j - 1;
+            pv0 = __shfl_sync(0xffffffffu, e0, lj); pv1 = __shfl_sync(0xffffffffu, e1, lj); pv2 = __shfl_sync(0xffffffffu, e2, lj);
+            pv3 = __shfl_sync(0xffffffffu, e3, lj); pv4 = __shfl_sync(0xffffffffu, e4, lj); pvc = __shfl_sync(0xffffffffu, cnt, lj);
+        }
+        if (nhit < nb) done = true;                            // a block of the round is not in the index
+        const bool more = !done && has_more;
+        PromptState& ps = pst_cur[p];
+        if ((uint32_t)lane < k) { ps.sc[lane] = mysc; ps.pod[lane] = (uint16_t)mypod; ps.bt[lane] = (uint8_t)mybt; }
+        if (lane == 0) {
+            ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
+            ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
+            rb.fate[li] = more ? kFateMore : kFateDone; rb.nwalk[i] = (uint8_t)nwalk;
+            if (more) { rb.src[p] = p; rb.pos[p] = (round > 0 ? rb.pos[p] : 0u) + (uint32_t)nb; }
+        }
+        if (more) { if (lane == nb - 1) rb.hstate[p] = key; }   // chain state for the next round: key of the round's last block
+        else {
+            if (a.dense) {
+                double* row = a.dense + (long long)p * t.max_pods;
+                const uint32_t P = t.max_pods;
+                if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                    for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) *reinterpret_cast<double2*>(row + c2) = make_double2(-1.0, -1.0);
+                } else {
+                    for (uint32_t c2 = lane; c2 < P; c2 += 32) row[c2] = -1.0;
+                }
+                __syncwarp();
+                if ((uint32_t)lane < k && mypod < P) row[mypod] = mysc;
+            }
+            if (a.sp_cnt) {
+                if ((uint32_t)lane < k) { a.sp_pods[(long long)p * kMaxEnt + lane] = (uint16_t)mypod; a.sp_scores[(long long)p * kMaxEnt + lane] = mysc; }
+                if (lane == 0) a.sp_cnt[p] = (uint8_t)k;
+            }
+            if (a.has_keys && lane == 0) a.has_keys[p] = (round > 0) || nb > 0;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- kernel R: followers take their representative's outcome --------------------------------------------------
 // Lane per follower.  Representative continues: so does the follower, with the representative's chain state, and its
 // walk state stays where the representative left it (src).  Representative finished: same pods, same scores -- the warp
 // writes the follower's result from the representative's final state.
 __global__ void __launch_bounds__(256)
-resolve_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+resolve_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int reps_too) {
     const int lane = threadIdx.x & 31;
+    if (reps_too) {                                            // representatives that continue (walk_round_kernel leaves the list to us)
+        const unsigned int n_a = rb.n_hl[0];
+        const unsigned int tw = gridDim.x * (blockDim.x / 32);
+        for (unsigned int w = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_a; w += tw) {
+            const unsigned int i = w * 32u + lane;
+            const unsigned int li = i < n_a ? rb.hl[i] : 0u;
+            const bool more = i < n_a && rb.fate[li] == kFateMore;
+            const uint32_t mm = __ballot_sync(0xffffffffu, more);
+            if (!mm) continue;
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (more) { const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u)); const uint32_t pp = rb.act[cur][li]; rb.act[cur ^ 1][ns] = pp; rb.lslot[pp] = ns; }
+        }
+    }
     const unsigned int n_fl = rb.n_hl[1];
     const PromptState* pst_cur = rb.pst[round & 1];
     const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
@@ -551,9 +918,9 @@ resolve_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, c
             if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (more) {
-                rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
+                { const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u)); rb.act[cur ^ 1][ns] = p; rb.lslot[p] = ns; }
                 rb.src[p] = pl;
-                rb.hstate[p] = rb.hstate[pl];
+                rb.hstate[p] = rb.hstate[pl]; rb.pos[p] = rb.pos[pl];
             }
         }
         uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
@@ -583,6 +950,151 @@ resolve_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, c
     }
 }
 
+// ---- kernel D: partial followers leave their class inside the chunk ----------------------------------------------
+// Lane per partial follower.  It shares the first d blocks of the chunk with representative R (same walk state before,
+// same tokens): if R's walk ended inside those blocks, so does this one, with R's result.  Otherwise it resumes from
+// R's snapshot after block d-1 and R's key of that block, and walks the rest of its chunk by itself -- hash one block,
+// probe it, score it (the order of the fused kernel) -- which normally ends at the first block it does not share.
+__device__ __forceinline__ uint64_t hash_block16(uint64_t parent, const uint32_t* __restrict__ tk) {
+    Fnv f;
+    f.begin_block(parent, 16);
+    if ((reinterpret_cast<uintptr_t>(tk) & 15u) == 0) {
+        const uint4* t4 = reinterpret_cast<const uint4*>(tk);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { const uint4 v = __ldg(t4 + c); f.token(v.x); f.token(v.y); f.token(v.z); f.token(v.w); }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) f.token(__ldg(tk + c));
+    }
+    return f.end_block();
+}
+constexpr int kDetachBlocks = 3;          // blocks a partial follower walks alone inside the round before it is re-queued
+struct DetachSmem { double sc[256 / 32][kMaxEnt][32]; uint16_t pod[256 / 32][kMaxEnt][32]; };
+template <int BS>
+__global__ void __launch_bounds__(256)
+detach_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int trace) {
+    __shared__ DetachSmem sm;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int n_dl = rb.n_hl[2];
+    const PromptState* pst_rd = rb.pst[round & 1];
+    PromptState* pst_cur = rb.pst[round & 1];
+    const size_t kstride = (size_t)a.n_prompts;
+    const bool peer = t.shard_bits != 0;
+    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
+    for (unsigned int w = blockIdx.x * (blockDim.x / 32) + wid; w * 32u < n_dl; w += total_warps) {
+        const unsigned int f = w * 32u + lane;
+        const bool have = f < n_dl;
+        uint32_t p = 0, meta = 0;
+        bool more = false;
+        ScoreState s; s.k = 0; s.alive = 0;
+        uint64_t h = 0;
+        uint32_t pos0 = 0, adv = 0;
+        if (have) {
+            const uint4 rc = __ldg(rb.drec + f);
+            p = rc.x; meta = rc.z & 0xffffu;
+            const unsigned int lr = rc.y;
+            const int d = (int)(rc.z >> 16);
+            const uint32_t pl = rc.w;
+            const unsigned int ar = rb.apos[lr];
+            const int nb = (int)(meta & 63u);
+            const PromptState& R = pst_rd[pl];
+            s.k = R.k;
+            for (uint32_t q = 0; q < s.k; ++q) s.pod[q] = R.pod[q];
+            if ((int)rb.nwalk[ar] < d) {                       // R stopped inside the shared blocks: same stop, same scores
+                for (uint32_t q = 0; q < s.k; ++q) s.sc[q] = R.sc[q];
+            } else {
+                const int j0 = rb.snap_run[(size_t)ar * kRoundBlocks + (size_t)(d - 1)];
+                const size_t sj = (size_t)ar * kRoundBlocks + (size_t)j0;
+                s.alive = rb.snap_alive[sj];
+                for (uint32_t q = 0; q < s.k; ++q) {
+                    double v = rb.snap_sc[sj * kMaxEnt + q];
+                    if (j0 < d - 1 && ((s.alive >> q) & 1u)) {          // later blocks of the run: the same addend again, in order
+                        const uint32_t bt = rb.snap_bt[sj * kMaxEnt + q];
+                        const double add = bt == 0xffu ? 0.0 : t.weight[bt & 15u];
+                        for (int u = j0; u < d - 1; ++u) v = __dadd_rn(v, add);
+                    }
+                    s.sc[q] = v;
+                }
+                h = rb.keys[(size_t)(d - 1) * kstride + ar];
+                const uint32_t mdl = a.model ? a.model[p] : a.model0;
+                pos0 = round > 0 ? rb.pos[p] : 0u;
+                const uint32_t* tk = a.tok + (a.tok_off[p] - a.tok_base) + (int64_t)pos0 * BS;
+                bool walking = true;
+                const int bend = min(nb, d + kDetachBlocks);          // walk at most this far alone; the rest waits for the next round
+                uint64_t hk = d < nb ? hash_block16(h, tk + (size_t)d * BS) : 0ull;       // key of the first block of its own
+                int b = d;
+                for (; b < bend; ++b) {
+                    if (trace) atomicAdd(&rb.n_hl[3], 1u);
+                    const uint64_t hm = home_of(hk, mdl);
+                    const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
+                    uint64_t slot = hm & t.req_mask & ~1ull;
+                    uint4 A0, B0, A1, B1;
+                    ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+                    // the next key does not depend on the probe: hash it while the probe is in flight
+                    const uint64_t hn = b + 1 < nb ? hash_block16(hk, tk + (size_t)(b + 1) * BS) : 0ull;
+                    SlotWords sw;
+                    bool hit;
+                    for (;;) {
+                        sw.a = A0; sw.b = B0;
+                        hit = slot_matches(sw.a, sw.b, hk, mdl);
+                        bool stop = hit || meta_state(sw.b.w) == kStateEmpty;
+                        if (!stop) { sw.a = A1; sw.b = B1; hit = slot_matches(sw.a, sw.b, hk, mdl); stop = hit || meta_state(sw.b.w) == kStateEmpty; }
+                        if (stop) break;
+                        slot = (slot + 2) & t.req_mask;                 // rare: displaced past the home pair
+                        ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+                    }
+                    if (!hit) { walking = false; break; }
+                    s.next(t, sw);
+                    if (!s.alive) { walking = false; break; }
+                    h = hk; hk = hn;
+                }
+                more = walking && (b < nb || ((meta >> 8) & 1u));
+                adv = (uint32_t)b;
+            }
+        }
+        // continue on its own next round, or write the result
+        const uint32_t mm = __ballot_sync(0xffffffffu, more);
+        if (mm) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (more) {
+                { const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u)); rb.act[cur ^ 1][ns] = p; rb.lslot[p] = ns; }
+                rb.hstate[p] = h; rb.src[p] = p; rb.pos[p] = pos0 + adv;
+                PromptState& ps = pst_cur[p];
+                ps.k = (uint8_t)s.k; ps.alive = (uint16_t)s.alive;
+                ps.pat[5] = 0xffffffffu;                        // no cached slot pattern: the next block is scored the long way
+                for (uint32_t q = 0; q < s.k; ++q) { ps.sc[q] = s.sc[q]; ps.pod[q] = s.pod[q]; ps.bt[q] = 0xffu; }
+            }
+        }
+        for (uint32_t q = 0; q < s.k; ++q) { sm.sc[wid][q][lane] = s.sc[q]; sm.pod[wid][q][lane] = s.pod[q]; }
+        __syncwarp();
+        uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
+        while (dm) {
+            const int l = __ffs(dm) - 1; dm &= dm - 1;
+            const uint32_t pp = __shfl_sync(0xffffffffu, p, l);
+            const uint32_t pk = __shfl_sync(0xffffffffu, s.k, l);
+            if (a.dense) {
+                double* row = a.dense + (long long)pp * t.max_pods;
+                const uint32_t P = t.max_pods;
+                if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                    for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
+                } else {
+                    for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
+                }
+                __syncwarp();
+                if ((uint32_t)lane < pk) { const uint32_t pd = sm.pod[wid][lane][l]; if (pd < P) row[pd] = sm.sc[wid][lane][l]; }
+            }
+            if (a.sp_cnt) {
+                if ((uint32_t)lane < pk) { a.sp_pods[(long long)pp * kMaxEnt + lane] = sm.pod[wid][lane][l]; a.sp_scores[(long long)pp * kMaxEnt + lane] = sm.sc[wid][lane][l]; }
+                if (lane == 0) a.sp_cnt[pp] = (uint8_t)pk;
+            }
+            if (a.has_keys && lane == 0) a.has_keys[pp] = 1;
+        }
+        __syncwarp();
+    }
+}
+
 // List setup + a 64-bit fingerprint of every prompt's first block.  The batch is then radix-sorted by fingerprint so
 // that prompts sharing a prefix sit in neighbouring lanes: their probes are the same 64-byte segments, which the
 // load unit merges within a warp and L2 serves across warps.  (Any order gives the same results; this one lets the
@@ -606,12 +1118,13 @@ __global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsig
     }
     nb = __reduce_max_sync(0xffffffffu, (unsigned)min(nb, 0xffffffffull));
     if ((threadIdx.x & 31) == 0 && nb) atomicMax(max_blocks, nb);
-    if (i == 0) for (int q = 0; q < kMaxParts; ++q) { cnt[4 * q] = ps.n[q]; cnt[4 * q + 1] = 0; }      // live-list lengths per part
+    if (i == 0) for (int q = 0; q < kMaxParts; ++q) { cnt[8 * q] = ps.n[q]; cnt[8 * q + 1] = 0; }      // live-list lengths per part
 }
 
 inline int rounds_init() {
     if (cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(probe_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(group_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)) != cudaSuccess) return -1;
     return 0;
 }
 

@@ -97,13 +97,15 @@ struct kvidx {
     int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
-    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate;
+    DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate, r_anch, r_snap, r_rec;
+    int rounds_trace = 0;
+    int rounds_walk = 1;           // kernel P: 1 warp per representative, 0 lane per representative
     int rounds_parts = 2;          // parts (streams) a large batch is split into
-    int rounds_dedup = 1;          // chunk-level prefix sharing in the round pipeline
+    int rounds_dedup = 2;          // round pipeline: 0 every prompt on its own, 1 prefix classes, 2 + partial followers
     int sort_prefix = 1;           // sort the batch by first-block fingerprint before the rounds
     int rounds_overlap = 1;        // run the two halves of a large batch on two streams
     int64_t rounds_overlap_min = 65536;
-    cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr}; cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t aux_stream[kMaxParts - 1] = {}; cudaEvent_t ev_fork = nullptr, ev_join[kMaxParts - 1] = {};
 };
 
 namespace {
@@ -212,32 +214,46 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
                         int64_t max_blocks) {
     CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(512));
     CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState) * 2));
-    CK(x->r_nbr.need((size_t)n * 4)); CK(x->r_role.need((size_t)n * 4)); CK(x->r_hl.need((size_t)n * 4 * 2)); CK(x->r_src.need((size_t)n * 4));
-    CK(x->r_fate.need((size_t)n));
+    CK(x->r_nbr.need((size_t)n * 4 * 2)); CK(x->r_role.need((size_t)n * 4)); CK(x->r_hl.need((size_t)n * 4 * 2)); CK(x->r_src.need((size_t)n * 4));
+    CK(x->r_fate.need((size_t)n * 4));      // fate, nfol, need_snap, dmin
+    CK(x->r_anch.need((size_t)n * 4 * 4));  // anch, apos, dl, lslot
+    CK(x->r_rec.need((size_t)n * 16 * 2));  // rec, drec
+    CK(x->r_snap.need((size_t)n * (kRoundBlocks * kMaxEnt * 8 + kRoundBlocks * 2 + 1 + kRoundBlocks + kRoundBlocks * kMaxEnt)));
     int np = 1;
     if (x->rounds_overlap && n >= x->rounds_overlap_min) np = std::max(1, std::min(kMaxParts, x->rounds_parts));
-    int64_t psz[kMaxParts] = {0, 0, 0, 0}, poff[kMaxParts] = {0, 0, 0, 0};
+    int64_t psz[kMaxParts] = {}, poff[kMaxParts] = {};
     {
         const int64_t per = ((n + np - 1) / np + 31) & ~31ll;
         int64_t at = 0;
         for (int q = 0; q < np; ++q) { poff[q] = at; psz[q] = std::max<int64_t>(0, std::min(per, n - at)); at += psz[q]; }
     }
     const uint64_t map_slots = pow2ceil((uint64_t)std::max<int64_t>(4 * ((n + np - 1) / np), 1024));
-    CK(x->r_map.need(map_slots * 4 * np));
+    CK(x->r_map.need((map_slots * 4 + (size_t)((n + np - 1) / np + 32) * 4) * np));      // election map + grp, cleared together
     unsigned int* cnt = x->r_cnt.as<unsigned int>();
-    unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(cnt + 32);
+    unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(cnt + 8 * kMaxParts);
     RoundBufs rb[kMaxParts]{};
     for (int q = 0; q < np; ++q) {
         const int64_t off = poff[q];
         rb[q].act[0] = x->r_act0.as<uint32_t>() + off; rb[q].act[1] = x->r_act1.as<uint32_t>() + off;
-        rb[q].n_act = cnt + 4 * q;
-        rb[q].n_hl = cnt + 4 * q + 2;
+        rb[q].n_act = cnt + 8 * q;
+        rb[q].n_hl = cnt + 8 * q + 2;
         rb[q].hstate = x->r_hstate.as<uint64_t>(); rb[q].src = x->r_src.as<uint32_t>();
         rb[q].pst[0] = x->r_pst.as<PromptState>(); rb[q].pst[1] = x->r_pst.as<PromptState>() + n;
-        rb[q].keys = x->r_keys.as<uint64_t>() + off; rb[q].nbr = x->r_nbr.as<uint32_t>() + off;
+        rb[q].keys = x->r_keys.as<uint64_t>() + off; rb[q].nbr = x->r_nbr.as<uint32_t>() + off; rb[q].pos = x->r_nbr.as<uint32_t>() + n;
         rb[q].role = x->r_role.as<uint32_t>() + off; rb[q].fate = x->r_fate.as<uint8_t>() + off;
+        rb[q].nfol = x->r_fate.as<uint8_t>() + n + 2 * off; rb[q].need_snap = rb[q].nfol + psz[q];      // adjacent: one memset per round
+        rb[q].dmin = x->r_fate.as<uint8_t>() + 3 * n + off;
+        rb[q].anch = x->r_anch.as<uint32_t>() + off; rb[q].apos = x->r_anch.as<uint32_t>() + n + off; rb[q].dl = x->r_anch.as<uint32_t>() + 2 * n + off; rb[q].lslot = x->r_anch.as<uint32_t>() + 3 * n;
+        rb[q].rec = x->r_rec.as<uint4>() + off; rb[q].drec = x->r_rec.as<uint4>() + n + off;
+        rb[q].snap_sc = x->r_snap.as<double>() + (size_t)off * kRoundBlocks * kMaxEnt;
+        rb[q].snap_alive = reinterpret_cast<uint16_t*>(x->r_snap.as<double>() + (size_t)n * kRoundBlocks * kMaxEnt) + (size_t)off * kRoundBlocks;
+        uint8_t* snap_bytes = reinterpret_cast<uint8_t*>(reinterpret_cast<uint16_t*>(x->r_snap.as<double>() + (size_t)n * kRoundBlocks * kMaxEnt) + (size_t)n * kRoundBlocks);
+        rb[q].nwalk = snap_bytes + off;
+        rb[q].snap_run = snap_bytes + n + (size_t)off * kRoundBlocks;
+        rb[q].snap_bt = snap_bytes + n + (size_t)n * kRoundBlocks + (size_t)off * kRoundBlocks * kMaxEnt;
         rb[q].hl = x->r_hl.as<uint32_t>() + off; rb[q].fl = x->r_hl.as<uint32_t>() + n + off;
-        rb[q].map = x->r_map.as<uint32_t>() + (size_t)q * map_slots; rb[q].map_mask = (uint32_t)(map_slots - 1);
+        rb[q].map = x->r_map.as<uint32_t>() + (size_t)q * (map_slots + (size_t)((n + np - 1) / np + 32)); rb[q].map_mask = (uint32_t)(map_slots - 1);
+        rb[q].grp = rb[q].map + map_slots;
     }
     ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
     CK(cudaMemsetAsync(x->r_cnt.p, 0, 512, st));
@@ -263,8 +279,11 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         max_blocks = (int64_t)mb;
     }
     int64_t rounds = (max_blocks + kRoundBlocks - 1) / kRoundBlocks;
+    if (x->rounds_dedup >= 2) rounds += 1;            // a prompt that left its class mid-chunk runs unaligned from there: one more round
     if (rounds < 1) rounds = 1;                       // round 0 also retires the prompts that have no full block
-    cudaStream_t strm[kMaxParts] = {st, x->aux_stream[0], x->aux_stream[1], x->aux_stream[2]};
+    cudaStream_t strm[kMaxParts];
+    strm[0] = st;
+    for (int q = 1; q < kMaxParts; ++q) strm[q] = x->aux_stream[q - 1];
     if (np > 1) {
         CK(cudaEventRecord(x->ev_fork, st));
         for (int q = 1; q < np; ++q) CK(cudaStreamWaitEvent(strm[q], x->ev_fork, 0));
@@ -275,19 +294,35 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         for (int q = 0; q < np; ++q) {
             const int64_t m = psz[q];
             if (m <= 0) continue;
-            CK(cudaMemsetAsync(rb[q].map, 0xff, map_slots * 4, strm[q]));
-            CK(cudaMemsetAsync(rb[q].n_hl, 0, 8, strm[q]));
-            const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads - 1) / kGroupThreads, (int64_t)x->sm_count * (np == 1 ? 8 : 4));
-            group_round_kernel<16><<<ggrid, kGroupThreads, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
+            CK(cudaMemsetAsync(rb[q].map, 0xff, (map_slots + (size_t)m) * 4, strm[q]));
+            CK(cudaMemsetAsync(rb[q].n_hl, 0, 16, strm[q]));
+            CK(cudaMemsetAsync(rb[q].nfol, 0, (size_t)m * 2, strm[q]));
+            const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads - 1) / kGroupThreads, (int64_t)x->sm_count * (np == 1 ? 3 : 2));
+            group_round_kernel<16><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
+            const unsigned lgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : 4));
+            group_lists_kernel<16><<<lgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2);
             const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * per_sm);
             hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
             const unsigned pgrid = (unsigned)std::min<int64_t>((m + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * per_sm);
-            probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
-            if (x->rounds_dedup) {
-                const unsigned rgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * 2);
-                resolve_round_kernel<<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
+            if (x->rounds_walk == 1) {
+                const unsigned wgrid = (unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)x->sm_count * (np == 1 ? 8 : 4));
+                walk_round_kernel<<<wgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
+            } else {
+                probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
             }
-            x->launches += x->rounds_dedup ? 4 : 3;
+            if (x->rounds_dedup || x->rounds_walk == 1) {
+                const unsigned rgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : 4));
+                resolve_round_kernel<<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_walk == 1);
+                if (x->rounds_dedup >= 2) detach_round_kernel<16><<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_trace);
+            }
+            x->launches += 4 + ((x->rounds_dedup || x->rounds_walk == 1) ? 1 : 0) + (x->rounds_dedup >= 2 ? 1 : 0);
+            if (x->rounds_trace) {      // debugging aid: list sizes of this round (synchronises)
+                unsigned int c[8];
+                CK(cudaMemcpyAsync(c, rb[q].n_act, sizeof c, cudaMemcpyDeviceToHost, strm[q]));
+                CK(cudaStreamSynchronize(strm[q]));
+                fprintf(stderr, "[kvidx rounds] round %lld part %d: live %u -> representatives %u, followers %u, partial %u (%u blocks walked alone) -> next %u\n",
+                        (long long)r, q, c[cur], c[2], c[3], c[4], c[5], c[cur ^ 1]);
+            }
         }
     }
     CK(cudaGetLastError());
@@ -532,7 +567,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     CK(cudaStreamCreateWithFlags(&x->own_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking));
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < kMaxParts - 1; ++q) {
         CK(cudaStreamCreateWithFlags(&x->aux_stream[q], cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&x->ev_join[q], cudaEventDisableTiming));
     }
@@ -578,8 +613,10 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
     if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_WALK")) x->rounds_walk = !strcmp(k, "lane") ? 0 : 1;
+    if (const char* k = getenv("KVIDX_ROUNDS_TRACE")) x->rounds_trace = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
-    if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
     if (rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = score_tuned_init();
@@ -599,7 +636,7 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_done[i]) cudaEventDestroy(x->ev_done[i]);
         if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]);
     }
-    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release(); x->r_role.release(); x->r_hl.release(); x->r_map.release(); x->r_src.release(); x->r_fate.release();
+    x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release(); x->r_role.release(); x->r_hl.release(); x->r_map.release(); x->r_src.release(); x->r_fate.release(); x->r_anch.release(); x->r_snap.release(); x->r_rec.release();
     x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
     if (x->tv.req) cudaFree(x->tv.req);
     if (x->tv.eng) cudaFree(x->tv.eng);
@@ -609,7 +646,7 @@ void kvidx_destroy(kvidx_t* x) {
     if (x->own_stream) cudaStreamDestroy(x->own_stream);
     if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
     if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < kMaxParts - 1; ++q) {
         if (x->aux_stream[q]) cudaStreamDestroy(x->aux_stream[q]);
         if (x->ev_join[q]) cudaEventDestroy(x->ev_join[q]);
     }

@@ -283,12 +283,15 @@ def _select_path(monkeypatch, path):
     elif path == "rounds-nodedup":
         monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
         monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "0")
+    elif path == "rounds-classes":          # whole-chunk classes only, no partial followers
+        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
+        monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "1")
     else:
         monkeypatch.setenv("KVIDX_SCORE_PATH", path)
         monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP", "0")
 
 
-PATHS = ["v1", "fused", "rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-nodedup"]
+PATHS = ["v1", "fused", "rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-nodedup", "rounds-classes"]
 
 
 @pytest.mark.parametrize("kernel", PATHS)
@@ -346,7 +349,7 @@ def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
         assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
 
 
-@pytest.mark.parametrize("kernel", ["rounds", "rounds2", "rounds4", "rounds-nosort"])
+@pytest.mark.parametrize("kernel", ["rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-classes"])
 def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
     """The round pipeline lets a prompt reuse another prompt's keys when chain state and the next 32-block chunk are
     identical.  Few documents, thousands of prompts: exact duplicates, prefixes of every length (so the shared chunk is
@@ -356,6 +359,10 @@ def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
     rng = np.random.default_rng(77)
     BS, T, ND = 16, 2048 + 160, 6                       # 138 blocks: four full rounds and a 10-block one
     docs = rng.integers(0, 50000, size=(ND, T), dtype=np.uint32)
+    # documents 3..5 start like document 0 (37, 70 and 5 blocks) and then go their own -- indexed -- way: prompts on them
+    # leave the popular prefix in the middle of a chunk and keep hitting
+    for d, nshare in ((3, 37), (4, 70), (5, 5)):
+        docs[d, : nshare * BS] = docs[0, : nshare * BS]
     ix, co = _index_pair(capacity=1 << 12, max_pods=16)
     for d in range(ND):
         keys = ix.hash_keys(docs[d], np.array([0, T], np.int64))[0]
@@ -367,7 +374,7 @@ def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
             co.add(0, eng, keys[:nb], pt)
     prompts = []
     for i in range(4000):
-        d = docs[int(rng.integers(0, ND))]
+        d = docs[int(rng.integers(0, ND)) if i % 3 else 0]          # document 0 is the popular one
         kind = i % 5
         if kind == 0:
             pr = d.copy()                                                        # exact duplicate of a document
