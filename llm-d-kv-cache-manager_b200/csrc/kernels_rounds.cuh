@@ -84,6 +84,7 @@ struct RoundBufs {
     uint16_t* snap_alive;                // [n_hl][32] alive mask after block j (stored at run starts)
     uint8_t* snap_bt;                    // [n_hl][32][kMaxEnt] tier that gives pod q its addend (0xff: 0.0) (at run starts)
     double* snap_sc;                     // [n_hl][32][kMaxEnt] scores after block j (at run starts)
+    uint32_t part_size;                  // prompts in this part (rounded up to 32): length of the per-slot arrays
     uint32_t* map;                       // class election: bucket -> live slot (kRoleSelf = empty), cleared before every round
     uint32_t map_mask;
 };
@@ -127,7 +128,7 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     uint4 (*ring)[4][32] = reinterpret_cast<GroupSmem*>(smem_raw_g)->ring[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned int n_act = rb.n_act[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
+    if (blockIdx.x == 0 && threadIdx.x == 0) { rb.n_act[cur ^ 1] = 0; rb.n_hl[0] = 0; rb.n_hl[1] = 0; rb.n_hl[2] = 0; rb.n_hl[3] = 0; }   // lists built below / by G2
     const unsigned int total_warps = gridDim.x * (kGroupThreads / 32);
     for (unsigned int w = blockIdx.x * (kGroupThreads / 32) + (threadIdx.x >> 5); w * 32u < n_act; w += total_warps) {
         const unsigned int i = w * 32u + lane;
@@ -420,6 +421,13 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned int n_hl = rb.n_hl[0];                                 // representatives this round (kernel G)
+    {   // the election map, grp and nfol are dead until the next round's kernel G: clear them here instead of three memsets
+        uint4* m4 = reinterpret_cast<uint4*>(rb.map);
+        const size_t nm = ((size_t)rb.map_mask + 1 + rb.part_size) / 4;   // map + grp are contiguous; sizes are multiples of 4 words
+        for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < nm; x += (size_t)gridDim.x * blockDim.x) m4[x] = make_uint4(~0u, ~0u, ~0u, ~0u);
+        uint32_t* f4 = reinterpret_cast<uint32_t*>(rb.nfol);
+        for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < rb.part_size / 4; x += (size_t)gridDim.x * blockDim.x) f4[x] = 0u;
+    }
     const unsigned int total_warps = gridDim.x * (kHashThreads / 32);
     for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_hl; w += total_warps) {
         const unsigned int i = w * 32u + lane;                            // position in the representative list
@@ -882,9 +890,12 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
 // Lane per follower.  Representative continues: so does the follower, with the representative's chain state, and its
 // walk state stays where the representative left it (src).  Representative finished: same pods, same scores -- the warp
 // writes the follower's result from the representative's final state.
-__global__ void __launch_bounds__(256)
-resolve_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int reps_too) {
+__device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int reps_too) {
     const int lane = threadIdx.x & 31;
+    {   // kernel P is done with need_snap: clear it for the next round
+        uint32_t* f4 = reinterpret_cast<uint32_t*>(rb.need_snap);
+        for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < rb.part_size / 4; x += (size_t)gridDim.x * blockDim.x) f4[x] = 0u;
+    }
     if (reps_too) {                                            // representatives that continue (walk_round_kernel leaves the list to us)
         const unsigned int n_a = rb.n_hl[0];
         const unsigned int tw = gridDim.x * (blockDim.x / 32);
@@ -971,9 +982,7 @@ __device__ __forceinline__ uint64_t hash_block16(uint64_t parent, const uint32_t
 constexpr int kDetachBlocks = 3;          // blocks a partial follower walks alone inside the round before it is re-queued
 struct DetachSmem { double sc[256 / 32][kMaxEnt][32]; uint16_t pod[256 / 32][kMaxEnt][32]; };
 template <int BS>
-__global__ void __launch_bounds__(256)
-detach_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int trace) {
-    __shared__ DetachSmem sm;
+__device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int trace, DetachSmem& sm) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned int n_dl = rb.n_hl[2];
     const PromptState* pst_rd = rb.pst[round & 1];
@@ -1093,6 +1102,16 @@ detach_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, co
         }
         __syncwarp();
     }
+}
+
+// Kernels R and D in one launch (they work on different lists and neither reads what the other writes, except the next
+// live list, which both append to).
+template <int BS>
+__global__ void __launch_bounds__(256)
+finish_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int reps_too, const int detach, const int trace) {
+    __shared__ DetachSmem sm;
+    resolve_round(t, a, rb, cur, round, reps_too);
+    if (detach) detach_round<BS>(t, a, rb, cur, round, trace, sm);
 }
 
 // List setup + a 64-bit fingerprint of every prompt's first block.  The batch is then radix-sorted by fingerprint so

@@ -1,0 +1,353 @@
+// kernels_rounds_plain.cuh -- Score() for MEDIUM batches: alternating hash / walk rounds, every prompt on its own.
+//
+// Same reference path as kernels_score.cuh (GetPodScores steps 2-4, pkg/kvcache/indexer.go:141-163).  Two kernels per
+// round and nothing else:
+//
+//   round r, kernel H (hash_round_kernel):  prompts that are still on the consecutive-prefix walk hash their next
+//       kRoundBlocks blocks.  Lockstep, thin lanes (no score / probe state), the branch-free FNV/CBOR code at the
+//       pipe-saturating occupancy measured by scripts/ubench_hash.cu.  Keys go to a per-round buffer in HBM (8 B per
+//       block -- versus 64 B of tokens and 64 B of slot read).
+//   round r, kernel P (probe_round_kernel): lane per prompt, a warp walks 32 prompts in lockstep one block per
+//       iteration, the next block's slot pair in flight while this one is scored.  Prompts whose walk continues are
+//       appended to the next round's list.
+//
+// The batch is radix-sorted by a fingerprint of the first block so that prompts sharing a prefix sit in neighbouring
+// lanes and their probes coalesce.  kernels_rounds.cuh goes further for LARGE batches (it hashes and walks every
+// distinct prefix once); its per-round bookkeeping costs a fixed ~0.2 ms per round, which this path does not pay.
+// Results are bit-identical on every path (tests run all of them against the oracle).
+#pragma once
+#include <cuda_runtime.h>
+#include "kernels_score.cuh"
+#include "kernels_rounds.cuh"      // ld_slot_pair, ent_of
+
+namespace kvx {
+namespace plain {
+
+constexpr int kRoundBlocks = 32;         // blocks hashed per prompt per round (== lanes per warp in kernel P)
+constexpr int kHashThreads = 256;
+constexpr int kProbeThreads = 256;
+
+struct __align__(8) PromptState {        // walk state carried between rounds (only for prompts that continue)
+    double sc[kMaxEnt];
+    uint16_t pod[kMaxEnt];
+    uint32_t pat[6];                     // entry words + count of the last scored block's slot
+    uint16_t alive;                      // bitmask over [0,k)
+    uint8_t k;
+    uint8_t pad;
+    uint8_t bt[kMaxEnt];                 // tier giving pod q its max weight in that slot (0xff: 0.0)
+    uint8_t pad2[2];
+};
+
+struct RoundBufs {
+    uint32_t* act[2];                    // active prompt lists (ping-pong)
+    unsigned int* n_act;                 // [2] list lengths
+    uint64_t* hstate;                    // chain hash after the last hashed block, per prompt
+    uint64_t* keys;                      // [kRoundBlocks][n_prompts] keys of the current round, block-major: key of
+                                         // block j of list slot i at keys[j * n_prompts + i] (coalesced both ways)
+    uint32_t* nbr;                       // [n_act] per list slot: blocks hashed this round | (more blocks follow) << 8
+    PromptState* pst;                    // per prompt
+};
+
+constexpr int kHashChunk = 1;            // blocks staged per copy step (2 = 128-byte accesses was measured: fewer, longer DRAM
+                                         // accesses but only 24 resident warps/SM -> 6 % slower; the kernel is pipe bound)
+template <int BS> struct HashSmem {
+    static constexpr int kRow = kHashChunk * BS * 4 + 16;   // 144 B: the four LDS.128 of a block stay conflict free
+    unsigned char tok[kHashThreads / 32][2][32 * kRow];
+};
+
+// ---- kernel H ---------------------------------------------------------------------------------
+template <int BS>
+__global__ void __launch_bounds__(kHashThreads, 4)
+hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+    static_assert(BS == 16, "staging pattern is written for 16-token blocks");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using SM = HashSmem<BS>;
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int n_act = rb.n_act[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
+    const unsigned int total_warps = gridDim.x * (kHashThreads / 32);
+    for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
+        const unsigned int i = w * 32u + lane;                            // slot in the active list
+        const bool have = i < n_act;
+        const uint32_t p = have ? rb.act[cur][i] : 0u;
+        int nb = 0;                                                      // blocks of this prompt in this round
+        const uint32_t* src = nullptr;
+        bool aligned = true;
+        uint64_t h = 0;
+        if (have) {
+            const int64_t b = a.tok_off[p] - a.tok_base, e = a.tok_off[p + 1] - a.tok_base;
+            const int64_t nblk = (e - b) / BS;
+            const int64_t first = (int64_t)round * kRoundBlocks;
+            nb = (int)max((int64_t)0, min((int64_t)kRoundBlocks, nblk - first));
+            rb.nbr[i] = (uint32_t)nb | ((first + nb < nblk) ? 0x100u : 0u);
+            src = a.tok + b + first * BS;
+            aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+            h = round == 0 ? t.init_hash : rb.hstate[p];
+        }
+        const int nb_max = __reduce_max_sync(0xffffffffu, nb);
+        // stage chunk c (kHashChunk blocks) of every lane's prompt: 4*kHashChunk lanes move one prompt's contiguous bytes.
+        auto stage = [&](int s, int c) {
+            const int b0 = c * kHashChunk;
+            const bool issue = b0 < nb;
+            const int nbytes = issue ? min(kHashChunk, nb - b0) * BS * 4 : 0;
+            const unsigned long long srcv = (issue && aligned) ? (unsigned long long)(uintptr_t)(src + (size_t)b0 * BS) : 0ull;
+            __syncwarp();
+            constexpr int LPP = 4 * kHashChunk;             // lanes that move one prompt's chunk (16 B each)
+            constexpr int PPI = 32 / LPP;                   // prompts per copy instruction
+#pragma unroll
+            for (int r = 0; r < 32 / PPI; ++r) {
+                const int q = PPI * r + lane / LPP;
+                const unsigned long long sp = __shfl_sync(0xffffffffu, srcv, q);
+                const int nby = kHashChunk == 1 ? BS * 4 : __shfl_sync(0xffffffffu, nbytes, q);
+                if (sp && (lane % LPP) * 16 < nby)
+                    cp_async_16(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane % LPP) * 16]), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16);
+            }
+            cp_async_commit();
+            if (issue && !aligned) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tok[wid][s][lane * SM::kRow]);
+                const uint32_t* g = src + (size_t)b0 * BS;
+                for (int j = 0; j < nbytes / 4; ++j) dst[j] = __ldg(g + j);
+            }
+        };
+        stage(0, 0);
+        const int nchunks = (nb_max + kHashChunk - 1) / kHashChunk;
+        for (int c = 0; c < nchunks; ++c) {
+            stage((c + 1) & 1, c + 1);
+            cp_async_wait<1>();
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < kHashChunk; ++u) {
+                const int b = c * kHashChunk + u;
+                Fnv f;
+                f.begin_block(h, BS);
+                const uint4* tp = reinterpret_cast<const uint4*>(&sm.tok[wid][c & 1][lane * SM::kRow + u * BS * 4]);
+                const uint4 v0 = tp[0], v1 = tp[1];
+                f.token(v0.x); f.token(v0.y); f.token(v0.z); f.token(v0.w);
+                const uint4 v2 = tp[2];
+                f.token(v1.x); f.token(v1.y); f.token(v1.z); f.token(v1.w);
+                const uint4 v3 = tp[3];
+                f.token(v2.x); f.token(v2.y); f.token(v2.z); f.token(v2.w);
+                f.token(v3.x); f.token(v3.y); f.token(v3.z); f.token(v3.w);
+                const uint64_t key = f.end_block();
+                if (b < nb) { h = key; rb.keys[(size_t)b * a.n_prompts + i] = key; }
+            }
+        }
+        cp_async_wait<0>();
+        __syncwarp();
+        if (have && nb > 0) rb.hstate[p] = h;
+    }
+}
+
+// ---- kernel P ---------------------------------------------------------------------------------
+// Kernel P, lane-per-prompt.  (Two warp-per-prompt versions came first -- 32 lanes probing a prompt's 32 keys at
+// once, then the same software-pipelined.  Both cost ~700 issue slots per prompt-round because the walk itself
+// runs on <= 10 lanes while the other 22 idle, and stayed at ~25 % issue utilisation: profiles/r1d_*.)  Here a
+// warp walks 32 prompts in lockstep, one block per iteration: every instruction serves 32 prompts, the 32 lanes'
+// probes are 32 independent 64-byte reads, and the slot pair for block j+1 is in flight while block j is scored.
+struct WalkSmem {
+    struct Warp {
+        double sc[kMaxEnt][32];
+        uint16_t pod[kMaxEnt][32];
+        uint8_t bt[kMaxEnt][32];
+    };
+    Warp w[kProbeThreads / 32];
+    double weight[16];
+};
+
+__global__ void __launch_bounds__(kProbeThreads, 4)
+probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+    extern __shared__ __align__(16) unsigned char smem_raw_w[];
+    WalkSmem& sm = *reinterpret_cast<WalkSmem*>(smem_raw_w);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WalkSmem::Warp& W = sm.w[wid];
+    if (threadIdx.x < 16) sm.weight[threadIdx.x] = t.weight[threadIdx.x];
+    __syncthreads();
+    const unsigned int n_act = rb.n_act[cur];
+    const size_t kstride = (size_t)a.n_prompts;
+    const bool peer = t.shard_bits != 0;
+    const unsigned int total_warps = gridDim.x * (kProbeThreads / 32);
+    for (unsigned int w = blockIdx.x * (kProbeThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
+        const unsigned int i = w * 32u + lane;
+        const bool have = i < n_act;
+        const uint32_t p = have ? rb.act[cur][i] : 0u;
+        const uint32_t meta = have ? rb.nbr[i] : 0u;
+        const int nb = (int)(meta & 63u);
+        const bool has_more = (meta >> 8) & 1u;
+        const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
+        uint32_t k = 0, alive = 0;
+        uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0;      // last scored pattern
+        if (round > 0 && have) {
+            const PromptState& ps = rb.pst[p];
+            k = ps.k; alive = ps.alive;
+            pv0 = ps.pat[0]; pv1 = ps.pat[1]; pv2 = ps.pat[2]; pv3 = ps.pat[3]; pv4 = ps.pat[4]; pvc = ps.pat[5];
+            for (uint32_t q = 0; q < k; ++q) { W.sc[q][lane] = ps.sc[q]; W.pod[q][lane] = ps.pod[q]; W.bt[q][lane] = ps.bt[q]; }
+        }
+        const uint64_t* frow = nullptr;
+        const int nb_max = __reduce_max_sync(0xffffffffu, nb);
+        bool done = !have || nb == 0;                          // walk ended (miss / no live pod); scores are final
+        // slot pair of block 0
+        // (An L2 prefetch running 8 blocks ahead of the walk was tried and made this kernel 2x slower -- DRAM reads
+        //  grew 50 % and issue utilisation fell to 11 %; profiles/r1d_*.  The SM's outstanding-miss capacity, not the
+        //  DRAM latency of a single chain, is what bounds it; the batch is sorted by prefix instead so that lanes of
+        //  a warp ask for the same slots.)
+        uint64_t key = 0, slot = 0;
+        const ReqSlot* base = t.req;                           // table (shard) of the current block's key
+        uint4 A0 = {0, 0, 0, 0}, B0 = {0, 0, 0, 0}, A1 = {0, 0, 0, 0}, B1 = {0, 0, 0, 0};
+        if (!done) {
+            key = rb.keys[i];
+            const uint64_t hm = home_of(key, mdl);
+            base = t.req_peer[shard_of(hm, t.shard_bits)]; slot = hm & t.req_mask & ~1ull;
+            ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+        }
+        uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + i] : 0ull;                         // key of block j+1
+        for (int j = 0; j < nb_max; ++j) {
+            // next block's pair is requested before this block is scored; keys are read one iteration ahead of their use
+            uint64_t nkey = key1, nslot = 0;
+            const ReqSlot* nbase = t.req;
+            uint4 nA0 = {0, 0, 0, 0}, nB0 = {0, 0, 0, 0}, nA1 = {0, 0, 0, 0}, nB1 = {0, 0, 0, 0};
+            const bool nextv = !done && (j + 1 < nb);
+            if (nextv) {
+                const uint64_t hm = home_of(nkey, mdl);
+                nbase = t.req_peer[shard_of(hm, t.shard_bits)]; nslot = hm & t.req_mask & ~1ull;
+                ld_slot_pair(nbase + nslot, peer, nA0, nB0, nA1, nB1);
+            }
+            key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + i] : 0ull;
+            if (!done && j < nb) {
+                uint4 A = A0, B = B0;
+                bool hit = slot_matches(A, B, key, mdl);
+                if (!hit && meta_state(B.w) != kStateEmpty) {
+                    A = A1; B = B1;
+                    hit = slot_matches(A, B, key, mdl);
+                    while (!hit && meta_state(B.w) != kStateEmpty) {          // rare: displaced past the home pair
+                        slot = (slot + 2) & t.req_mask;
+                        ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+                        A = A0; B = B0; hit = slot_matches(A, B, key, mdl);
+                        if (!hit && meta_state(B.w) != kStateEmpty) { A = A1; B = B1; hit = slot_matches(A, B, key, mdl); }
+                    }
+                }
+                if (!hit) { done = true; }
+                else {
+                    SlotWords sw; sw.a = A; sw.b = B;
+                    const uint32_t cnt = meta_count(B.w);
+                    const bool first_block = (round == 0 && j == 0);
+                    const bool same = !first_block && (((pv0 ^ A.z) | (pv1 ^ A.w) | (pv2 ^ B.x) | (pv3 ^ B.y) | (pv4 ^ B.z) | (pvc ^ cnt)) == 0u);
+                    if (same) {
+                        uint32_t am = alive;
+                        while (am) {
+                            const int q = __ffs(am) - 1; am &= am - 1;
+                            const uint32_t bt = W.bt[q][lane];
+                            const double mx = bt == 0xffu ? 0.0 : sm.weight[bt];
+                            W.sc[q][lane] = __dadd_rn(W.sc[q][lane], mx);
+                        }
+                    } else if (first_block) {
+                        // activePods := pods of block 0 (after the filter); score = max weight   (kvblock_scorer.go:118-128)
+                        frow = filter_row(a.filter, p, t.filter_words);
+                        k = 0;
+                        for (uint32_t e = 0; e < cnt; ++e) {
+                            const uint32_t pt = slot_ent(sw, e), pd = pt >> 4;
+                            if (frow && !filter_has(frow, pd)) continue;
+                            const double wt = sm.weight[pt & 15u];
+                            uint32_t q = 0;
+                            for (; q < k; ++q) if (W.pod[q][lane] == pd) break;
+                            if (q == k) { W.pod[k][lane] = (uint16_t)pd; W.sc[k][lane] = 0.0; W.bt[k][lane] = 0xffu; ++k; }
+                            if (wt > W.sc[q][lane]) { W.sc[q][lane] = wt; W.bt[q][lane] = (uint8_t)(pt & 15u); }
+                        }
+                        alive = (1u << k) - 1u;
+                    } else {
+                        // activePods &= pods(block); score[p] += max weight, in block order   (kvblock_scorer.go:130-147)
+                        uint32_t am = alive;
+                        while (am) {
+                            const int q = __ffs(am) - 1; am &= am - 1;
+                            const uint32_t want = W.pod[q][lane];
+                            double mx = 0.0; bool present = false; uint32_t bt = 0xffu;
+                            for (uint32_t e = 0; e < cnt; ++e) {
+                                const uint32_t pt = slot_ent(sw, e);
+                                if ((pt >> 4) == want) { present = true; const double wt = sm.weight[pt & 15u]; if (wt > mx) { mx = wt; bt = pt & 15u; } }
+                            }
+                            if (present) { W.sc[q][lane] = __dadd_rn(W.sc[q][lane], mx); W.bt[q][lane] = (uint8_t)bt; }
+                            else alive &= ~(1u << q);
+                        }
+                    }
+                    pv0 = A.z; pv1 = A.w; pv2 = B.x; pv3 = B.y; pv4 = B.z; pvc = cnt;
+                    if (!alive) done = true;
+                }
+            }
+            key = nkey; slot = nslot; base = nbase; A0 = nA0; B0 = nB0; A1 = nA1; B1 = nB1;
+        }
+        // ---- continue next round, or write the result ----
+        const bool more = have && !done && has_more;           // all blocks of the round hit, pods still live, blocks left
+        const uint32_t mm = __ballot_sync(0xffffffffu, more);
+        if (mm) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (more) {
+                rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
+                PromptState& ps = rb.pst[p];
+                ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
+                ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
+                for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; ps.bt[q] = W.bt[q][lane]; }
+            }
+        }
+        __syncwarp();
+        uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
+        while (dm) {                                           // the whole warp writes each finished prompt's row
+            const int l = __ffs(dm) - 1; dm &= dm - 1;
+            const uint32_t pp = __shfl_sync(0xffffffffu, p, l);
+            const uint32_t pk = __shfl_sync(0xffffffffu, k, l);
+            const uint32_t pmeta = __shfl_sync(0xffffffffu, meta, l);
+            if (a.dense) {
+                double* row = a.dense + (long long)pp * t.max_pods;
+                const uint32_t P = t.max_pods;
+                if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                    for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
+                } else {
+                    for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
+                }
+                __syncwarp();
+                if ((uint32_t)lane < pk) { const uint32_t pd = W.pod[lane][l]; if (pd < P) row[pd] = W.sc[lane][l]; }
+            }
+            if (a.sp_cnt) {
+                if ((uint32_t)lane < pk) { a.sp_pods[(long long)pp * kMaxEnt + lane] = W.pod[lane][l]; a.sp_scores[(long long)pp * kMaxEnt + lane] = W.sc[lane][l]; }
+                if (lane == 0) a.sp_cnt[pp] = (uint8_t)pk;
+            }
+            if (a.has_keys && lane == 0) a.has_keys[pp] = (round > 0) || (pmeta & 63u) > 0;
+        }
+        __syncwarp();
+    }
+}
+
+// List setup + a 64-bit fingerprint of every prompt's first block.  The batch is then radix-sorted by fingerprint so
+// that prompts sharing a prefix sit in neighbouring lanes: their probes are the same 64-byte segments, which the
+// load unit merges within a warp and L2 serves across warps.  (Any order gives the same results; this one lets the
+// prefix sharing the system exists for -- system prompts, shared documents -- show up as memory locality.)
+__global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsigned long long* max_blocks, uint64_t* fp, uint32_t* idx,
+                                   unsigned int* n_act, unsigned int n_first) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned long long nb = 0;
+    if (i < a.n_prompts) {
+        const int64_t b = a.tok_off[i] - a.tok_base, e = a.tok_off[i + 1] - a.tok_base;
+        nb = (unsigned long long)((e - b) / block_size);
+        uint64_t f = ~0ull;                                   // prompts without a full block sort last
+        if (nb > 0) {
+            f = 0x9E3779B97F4A7C15ull;
+            const uint32_t* tk = a.tok + b;
+            for (uint32_t j = 0; j < block_size && j < 16u; ++j) f = mix64(f ^ __ldg(tk + j));
+            f &= ~(1ull << 63);
+        }
+        fp[i] = f; idx[i] = (uint32_t)i;
+    }
+    nb = __reduce_max_sync(0xffffffffu, (unsigned)min(nb, 0xffffffffull));
+    if ((threadIdx.x & 31) == 0 && nb) atomicMax(max_blocks, nb);
+    if (i == 0) { n_act[0] = n_first; n_act[1] = 0; n_act[2] = (unsigned int)a.n_prompts - n_first; n_act[3] = 0; }
+}
+
+inline int rounds_init() {
+    if (cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(probe_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)) != cudaSuccess) return -1;
+    return 0;
+}
+
+}  // namespace plain
+}  // namespace kvx

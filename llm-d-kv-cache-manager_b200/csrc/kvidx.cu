@@ -15,6 +15,7 @@
 #include "kernels_write.cuh"
 #include "kernels_score.cuh"
 #include "kernels_rounds.cuh"
+#include "kernels_rounds_plain.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace kvx;
@@ -97,10 +98,11 @@ struct kvidx {
     int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
+    int64_t classes_min = 393216;  // ... and at least this large, the prefix-class round pipeline
     DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate, r_anch, r_snap, r_rec;
     int rounds_trace = 0;
     int rounds_walk = 1;           // kernel P: 1 warp per representative, 0 lane per representative
-    int rounds_parts = 2;          // parts (streams) a large batch is split into
+    int rounds_parts = 8;          // parts (streams) a large batch is split into
     int rounds_dedup = 2;          // round pipeline: 0 every prompt on its own, 1 prefix classes, 2 + partial followers
     int sort_prefix = 1;           // sort the batch by first-block fingerprint before the rounds
     int rounds_overlap = 1;        // run the two halves of a large batch on two streams
@@ -215,7 +217,8 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
     CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(512));
     CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState) * 2));
     CK(x->r_nbr.need((size_t)n * 4 * 2)); CK(x->r_role.need((size_t)n * 4)); CK(x->r_hl.need((size_t)n * 4 * 2)); CK(x->r_src.need((size_t)n * 4));
-    CK(x->r_fate.need((size_t)n * 4));      // fate, nfol, need_snap, dmin
+    const int64_t n_al = (n + 63) & ~63ll;
+    CK(x->r_fate.need((size_t)n_al * 4 + 64 * kMaxParts));      // fate, dmin, then per part nfol | need_snap
     CK(x->r_anch.need((size_t)n * 4 * 4));  // anch, apos, dl, lslot
     CK(x->r_rec.need((size_t)n * 16 * 2));  // rec, drec
     CK(x->r_snap.need((size_t)n * (kRoundBlocks * kMaxEnt * 8 + kRoundBlocks * 2 + 1 + kRoundBlocks + kRoundBlocks * kMaxEnt)));
@@ -228,7 +231,8 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         for (int q = 0; q < np; ++q) { poff[q] = at; psz[q] = std::max<int64_t>(0, std::min(per, n - at)); at += psz[q]; }
     }
     const uint64_t map_slots = pow2ceil((uint64_t)std::max<int64_t>(4 * ((n + np - 1) / np), 1024));
-    CK(x->r_map.need((map_slots * 4 + (size_t)((n + np - 1) / np + 32) * 4) * np));      // election map + grp, cleared together
+    const size_t gstride = map_slots + (size_t)((((n + np - 1) / np) + 32 + 3) & ~3ll);      // election map + grp per part, cleared together
+    CK(x->r_map.need(gstride * 4 * np));
     unsigned int* cnt = x->r_cnt.as<unsigned int>();
     unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(cnt + 8 * kMaxParts);
     RoundBufs rb[kMaxParts]{};
@@ -241,8 +245,9 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         rb[q].pst[0] = x->r_pst.as<PromptState>(); rb[q].pst[1] = x->r_pst.as<PromptState>() + n;
         rb[q].keys = x->r_keys.as<uint64_t>() + off; rb[q].nbr = x->r_nbr.as<uint32_t>() + off; rb[q].pos = x->r_nbr.as<uint32_t>() + n;
         rb[q].role = x->r_role.as<uint32_t>() + off; rb[q].fate = x->r_fate.as<uint8_t>() + off;
-        rb[q].nfol = x->r_fate.as<uint8_t>() + n + 2 * off; rb[q].need_snap = rb[q].nfol + psz[q];      // adjacent: one memset per round
-        rb[q].dmin = x->r_fate.as<uint8_t>() + 3 * n + off;
+        rb[q].part_size = (uint32_t)((psz[q] + 31) & ~31ll);
+        rb[q].nfol = x->r_fate.as<uint8_t>() + 2 * n_al + 2 * off + 64 * q; rb[q].need_snap = rb[q].nfol + rb[q].part_size;
+        rb[q].dmin = x->r_fate.as<uint8_t>() + n_al + off;
         rb[q].anch = x->r_anch.as<uint32_t>() + off; rb[q].apos = x->r_anch.as<uint32_t>() + n + off; rb[q].dl = x->r_anch.as<uint32_t>() + 2 * n + off; rb[q].lslot = x->r_anch.as<uint32_t>() + 3 * n;
         rb[q].rec = x->r_rec.as<uint4>() + off; rb[q].drec = x->r_rec.as<uint4>() + n + off;
         rb[q].snap_sc = x->r_snap.as<double>() + (size_t)off * kRoundBlocks * kMaxEnt;
@@ -252,7 +257,7 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         rb[q].snap_run = snap_bytes + n + (size_t)off * kRoundBlocks;
         rb[q].snap_bt = snap_bytes + n + (size_t)n * kRoundBlocks + (size_t)off * kRoundBlocks * kMaxEnt;
         rb[q].hl = x->r_hl.as<uint32_t>() + off; rb[q].fl = x->r_hl.as<uint32_t>() + n + off;
-        rb[q].map = x->r_map.as<uint32_t>() + (size_t)q * (map_slots + (size_t)((n + np - 1) / np + 32)); rb[q].map_mask = (uint32_t)(map_slots - 1);
+        rb[q].map = x->r_map.as<uint32_t>() + (size_t)q * gstride; rb[q].map_mask = (uint32_t)(map_slots - 1);
         rb[q].grp = rb[q].map + map_slots;
     }
     ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
@@ -284,6 +289,8 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
     cudaStream_t strm[kMaxParts];
     strm[0] = st;
     for (int q = 1; q < kMaxParts; ++q) strm[q] = x->aux_stream[q - 1];
+    CK(cudaMemsetAsync(x->r_map.p, 0xff, gstride * 4 * np, st));
+    CK(cudaMemsetAsync(x->r_fate.as<uint8_t>() + 2 * n_al, 0, (size_t)n_al * 2 + 64 * kMaxParts, st));     // nfol, need_snap
     if (np > 1) {
         CK(cudaEventRecord(x->ev_fork, st));
         for (int q = 1; q < np; ++q) CK(cudaStreamWaitEvent(strm[q], x->ev_fork, 0));
@@ -294,9 +301,6 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         for (int q = 0; q < np; ++q) {
             const int64_t m = psz[q];
             if (m <= 0) continue;
-            CK(cudaMemsetAsync(rb[q].map, 0xff, (map_slots + (size_t)m) * 4, strm[q]));
-            CK(cudaMemsetAsync(rb[q].n_hl, 0, 16, strm[q]));
-            CK(cudaMemsetAsync(rb[q].nfol, 0, (size_t)m * 2, strm[q]));
             const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads - 1) / kGroupThreads, (int64_t)x->sm_count * (np == 1 ? 3 : 2));
             group_round_kernel<16><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
             const unsigned lgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : 4));
@@ -310,12 +314,11 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
             } else {
                 probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
             }
-            if (x->rounds_dedup || x->rounds_walk == 1) {
+            {
                 const unsigned rgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : 4));
-                resolve_round_kernel<<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_walk == 1);
-                if (x->rounds_dedup >= 2) detach_round_kernel<16><<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_trace);
+                finish_round_kernel<16><<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_walk == 1, x->rounds_dedup >= 2, x->rounds_trace);
             }
-            x->launches += 4 + ((x->rounds_dedup || x->rounds_walk == 1) ? 1 : 0) + (x->rounds_dedup >= 2 ? 1 : 0);
+            x->launches += 5;
             if (x->rounds_trace) {      // debugging aid: list sizes of this round (synchronises)
                 unsigned int c[8];
                 CK(cudaMemcpyAsync(c, rb[q].n_act, sizeof c, cudaMemcpyDeviceToHost, strm[q]));
@@ -327,6 +330,72 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
     }
     CK(cudaGetLastError());
     for (int q = 1; q < np; ++q) { CK(cudaEventRecord(x->ev_join[q - 1], strm[q])); CK(cudaStreamWaitEvent(st, x->ev_join[q - 1], 0)); }
+    return 0;
+}
+
+// Medium batches: hash / walk rounds, every prompt on its own (kernels_rounds_plain.cuh); two halves on two streams.
+int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
+                        const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
+                        int64_t max_blocks) {
+    CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(64));
+    CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * plain::kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(plain::PromptState)));
+    CK(x->r_nbr.need((size_t)n * 4));
+    const bool overlap = x->rounds_overlap && n >= x->rounds_overlap_min;
+    const int64_t nA = overlap ? ((n / 2 + 31) & ~31ll) : n, nB = n - nA;
+    unsigned int* cnt = x->r_cnt.as<unsigned int>();
+    unsigned long long* d_maxb = reinterpret_cast<unsigned long long*>(x->r_cnt.as<unsigned char>() + 16);
+    plain::RoundBufs rb[2]{};
+    for (int hlf = 0; hlf < 2; ++hlf) {
+        const int64_t off = hlf ? nA : 0;
+        rb[hlf].act[0] = x->r_act0.as<uint32_t>() + off; rb[hlf].act[1] = x->r_act1.as<uint32_t>() + off;
+        rb[hlf].n_act = cnt + 2 * hlf;
+        rb[hlf].hstate = x->r_hstate.as<uint64_t>(); rb[hlf].pst = x->r_pst.as<plain::PromptState>();
+        rb[hlf].keys = x->r_keys.as<uint64_t>() + off; rb[hlf].nbr = x->r_nbr.as<uint32_t>() + off;
+    }
+    ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
+    CK(cudaMemsetAsync(x->r_cnt.p, 0, 64, st));
+    CK(x->r_fp.need((size_t)n * 8 * 2 + (size_t)n * 4));
+    uint64_t* fp_in = x->r_fp.as<uint64_t>(); uint64_t* fp_out = fp_in + n;
+    uint32_t* idx_in = reinterpret_cast<uint32_t*>(fp_out + n);
+    plain::rounds_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, x->tv.block_size, d_maxb, fp_in, x->sort_prefix ? idx_in : rb[0].act[0], cnt,
+                                                                    (unsigned int)nA);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    if (x->sort_prefix) {
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
+        CK(x->r_sort.need(tmp));
+        CK(cub::DeviceRadixSort::SortPairs(x->r_sort.p, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
+        x->launches += 6;     // cub: histogram + onesweep passes
+    }
+    if (max_blocks < 0) {
+        unsigned long long mb = 0;
+        CK(cudaMemcpyAsync(&mb, d_maxb, sizeof mb, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        max_blocks = (int64_t)mb;
+    }
+    int64_t rounds = (max_blocks + plain::kRoundBlocks - 1) / plain::kRoundBlocks;
+    if (rounds < 1) rounds = 1;                       // round 0 also retires the prompts that have no full block
+    cudaStream_t strm[2] = {st, x->aux_stream[0]};
+    const int nh = nB > 0 ? 2 : 1;
+    if (nh == 2) { CK(cudaEventRecord(x->ev_fork, st)); CK(cudaStreamWaitEvent(x->aux_stream[0], x->ev_fork, 0)); }
+    const int per_sm_h = nh == 2 ? 2 : 4, per_sm_p = nh == 2 ? 2 : 4;
+    for (int64_t r = 0; r < rounds; ++r) {
+        const int cur = (int)(r & 1);
+        for (int hlf = 0; hlf < nh; ++hlf) {
+            const int64_t m = hlf ? nB : nA;
+            const unsigned hgrid = (unsigned)std::min<int64_t>((m + plain::kHashThreads - 1) / plain::kHashThreads, (int64_t)x->sm_count * per_sm_h);
+            plain::hash_round_kernel<16><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+        }
+        for (int hlf = 0; hlf < nh; ++hlf) {
+            const int64_t m = hlf ? nB : nA;
+            const unsigned pgrid = (unsigned)std::min<int64_t>((m + plain::kProbeThreads - 1) / plain::kProbeThreads, (int64_t)x->sm_count * per_sm_p);
+            plain::probe_round_kernel<<<pgrid, plain::kProbeThreads, sizeof(plain::WalkSmem), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+        }
+        x->launches += 2 * nh;
+    }
+    CK(cudaGetLastError());
+    if (nh == 2) { CK(cudaEventRecord(x->ev_join[0], x->aux_stream[0])); CK(cudaStreamWaitEvent(st, x->ev_join[0], 0)); }
     return 0;
 }
 
@@ -344,8 +413,11 @@ int launch_score(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t 
         score_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
                                                                   o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, sb, stride);
         x->launches += 1;
-    } else if (x->tv.block_size == 16 && n < (1ll << 32) && (x->score_path == 2 || (x->score_path == 0 && n >= x->rounds_min))) {
-        return launch_score_rounds(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks);
+    } else if (x->tv.block_size == 16 && n < (1ll << 32) && (x->score_path >= 2 || (x->score_path == 0 && n >= x->rounds_min))) {
+        // path 2: plain rounds, 3: prefix classes; automatic: by batch size (the class pipeline has a fixed cost per round)
+        const bool classes = x->score_path == 3 || (x->score_path == 0 && n >= x->classes_min);
+        return classes ? launch_score_rounds(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks)
+                       : launch_score_rounds_plain(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks);
     } else {
         int rc = launch_score_tuned(x->tv, x->sm_count, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
                                     o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, &x->d_cnt->pad, st, &x->launches);
@@ -609,8 +681,9 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     t.req_peer[t.shard_rank] = t.req; t.eng_peer[t.shard_rank] = t.eng; t.cnt_peer[t.shard_rank] = t.cnt;
     CK(cudaStreamSynchronize(x->stream));
     if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
-    if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : 0;
+    if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : !strcmp(k, "classes") ? 3 : 0;
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
+    if (const char* k = getenv("KVIDX_CLASSES_MIN")) x->classes_min = atoll(k);
     if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_WALK")) x->rounds_walk = !strcmp(k, "lane") ? 0 : 1;
@@ -618,7 +691,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
-    if (rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    if (rounds_init() || plain::rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     rc = score_tuned_init();
     if (rc) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     *out = x;

@@ -191,7 +191,7 @@ def _random_stream(rng, n_steps, BS, P, NT, docs, model=0):
     return np.array(ev, EVENT_DTYPE), np.array(hs, np.uint64), np.array(tk, np.uint64).astype(np.uint32)
 
 
-@pytest.mark.parametrize("seed,BS,path", [(11, 16, "fused"), (12, 16, "rounds"), (13, 4, "fused"), (14, 16, "rounds")])
+@pytest.mark.parametrize("seed,BS,path", [(11, 16, "fused"), (12, 16, "rounds"), (13, 4, "fused"), (14, 16, "classes")])
 def test_random_event_stream_and_queries_vs_cpp_oracle(seed, BS, path, monkeypatch):
     """Differential test on a few thousand events (sequential replay => identical linearisation)."""
     _select_path(monkeypatch, path)
@@ -266,32 +266,35 @@ def test_batched_events_per_pod_order_vs_oracle():
 
 
 def _select_path(monkeypatch, path):
-    """v1: thread-per-prompt kernel; fused: persistent lane-worker kernel; rounds: hash/probe round pipeline
-    (one stream); rounds2: the same with the batch split over two streams; rounds-nosort: without the prefix sort."""
+    """v1: thread-per-prompt kernel; fused: persistent lane-worker kernel; rounds*: hash / walk rounds, every prompt on
+    its own (one stream / two halves on two streams / without the prefix sort); classes*: the round pipeline that hashes
+    and walks one representative per distinct prefix (one part / 2 / 8 parts / unsorted / sharing switched off / whole
+    chunks only, no partial followers / lane-per-representative walk kernel)."""
     if path == "v1":
         monkeypatch.setenv("KVIDX_SCORE_KERNEL", "v1")
-    elif path == "rounds2":
-        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
+        return
+    base, _, var = path.partition("-")
+    parts = base.lstrip("abcdefghijklmnopqrstuvwxyz")
+    base = base[: len(base) - len(parts)]
+    monkeypatch.setenv("KVIDX_SCORE_PATH", base)
+    if parts:
         monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP_MIN", "64")
-    elif path == "rounds4":
-        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
-        monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP_MIN", "64")
-        monkeypatch.setenv("KVIDX_ROUNDS_PARTS", "4")
-    elif path == "rounds-nosort":
-        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
-        monkeypatch.setenv("KVIDX_SORT_PREFIX", "0")
-    elif path == "rounds-nodedup":
-        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
-        monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "0")
-    elif path == "rounds-classes":          # whole-chunk classes only, no partial followers
-        monkeypatch.setenv("KVIDX_SCORE_PATH", "rounds")
-        monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "1")
+        monkeypatch.setenv("KVIDX_ROUNDS_PARTS", parts)
     else:
-        monkeypatch.setenv("KVIDX_SCORE_PATH", path)
         monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP", "0")
+    if var == "nosort":
+        monkeypatch.setenv("KVIDX_SORT_PREFIX", "0")
+    elif var == "nodedup":
+        monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "0")
+    elif var == "whole":
+        monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "1")
+    elif var == "lane":
+        monkeypatch.setenv("KVIDX_ROUNDS_WALK", "lane")
 
 
-PATHS = ["v1", "fused", "rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-nodedup", "rounds-classes"]
+ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "classes", "classes2", "classes8", "classes-nosort", "classes-nodedup", "classes-whole",
+               "classes4-lane"]
+PATHS = ["v1", "fused"] + ROUND_PATHS
 
 
 @pytest.mark.parametrize("kernel", PATHS)
@@ -315,7 +318,7 @@ def test_synth_config2_shape_vs_oracle_and_closed_form(kernel, monkeypatch):
     assert np.array_equal(s1, wl.expected_scores(doc, m))
 
 
-@pytest.mark.parametrize("kernel", ["fused", "rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-nodedup"])
+@pytest.mark.parametrize("kernel", ["fused"] + ROUND_PATHS)
 def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
     """Lane refill / round lists, unaligned prompt starts (per-lane staging fallback), empty and sub-block
     prompts, pod filters, against the oracle."""
@@ -349,7 +352,7 @@ def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
         assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
 
 
-@pytest.mark.parametrize("kernel", ["rounds", "rounds2", "rounds4", "rounds-nosort", "rounds-classes"])
+@pytest.mark.parametrize("kernel", ROUND_PATHS)
 def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
     """The round pipeline lets a prompt reuse another prompt's keys when chain state and the next 32-block chunk are
     identical.  Few documents, thousands of prompts: exact duplicates, prefixes of every length (so the shared chunk is

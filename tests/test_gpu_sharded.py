@@ -20,9 +20,9 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("path", ["fused", "rounds"])
+@pytest.mark.parametrize("path", ["fused", "rounds", "classes"])
 def test_two_shards_one_process(path, monkeypatch):
-    monkeypatch.setenv("KVIDX_SCORE_PATH", path)
+    monkeypatch.setenv("KVIDX_SCORE_PATH", path)   # fused | rounds | classes
     wl = synth.Workload(5, 1024, 1 << 14, 32)
     world = 2
     shards = [kvidx.Index(capacity=1 << 15, max_pods=32, device=r, shard_rank=r, shard_count=world) for r in range(world)]
