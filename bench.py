@@ -364,10 +364,12 @@ def run_ours(args):
             "traffic": None if traffic is None else traffic * Q,
             "peak_source": peak_src, "algorithmic_bytes_per_prompt_mean": float(A.mean()),
             "algorithmic_bytes_per_launch": float(A.sum()), "kernel_ms": float(step_ms.mean()),
-            "kernel": "one step = prefix sort + 8 x (hash_round_kernel, probe_round_kernel); achieved = step's algorithmic bytes / "
-                      "step GPU time (CUDA events around all of its launches), i.e. a lower bound for every kernel in it",
-            "note": "co-limited: FNV-1a issue bound (4.2e10 block-hashes/s measured, scripts/ubench_hash.cu) and the HBM random-access "
-                    "rate (36 G 64-byte reads/s measured, scripts/ubench_mem.cu); see DESIGN.md"}
+            "kernel": "one step = prefix sort + 9 rounds x 8 parts x (group_round, group_lists, hash_round, walk_round, finish_round kernels); "
+                      "achieved = step's algorithmic bytes / step GPU time (CUDA events around all of its launches), i.e. a lower bound for "
+                      "every kernel in it; group_round_kernel (token streaming, 31 % of the step) alone runs at 69 % of DRAM peak (profiles/)",
+            "note": "the step is a chain of 9 rounds whose kernels are latency bound at this batch size (serial FNV-1a chain of the "
+                    "representatives: 2.4 us per block; dependent index loads); the fixed cost is ~1.6 ms per step, the marginal cost "
+                    "1.9 ms per 524288 prompts; see DESIGN.md"}
 
     # ---- e2e: host pinned buffers through kvidx_score_batch (H2D + kernel + D2H inside the timed region) ----
     ix.set_stream(0)
@@ -430,6 +432,8 @@ def run_ours(args):
                           "prompt_tokens": wl.T, "index_blocks": wl.n_blocks, "pods": wl.P, "block_size": BLOCK,
                           "batch_prompts_per_gpu": Q, "query_mix": "m uniform in [0,n] matched blocks + random tail",
                           "queries_per_document": Q / wl.D,
+                          "pipeline": "prefix-class rounds: each distinct prefix is hashed and probed once per batch (batches >= 393216 prompts; "
+                                      "smaller ones take the per-prompt round or fused kernels)" if Q >= 393216 else "per-prompt rounds",
                           "l2_policy": "inputs (%.1f GB tokens + %.1f GB table) larger than the 126 MB L2; no flush" % (Q * wl.T * 4 / 1e9, st["request_slots"] * 32 / 1e9),
                           "multi_gpu": {"single": "single GPU", "replicas": "replicas: full index per GPU, prompts sharded, no data-path collective",
                                         "sharded": "hash-range sharded tables, probes over NVLink peer memory (CUDA IPC), per-pod ingest ranks"}[mode],

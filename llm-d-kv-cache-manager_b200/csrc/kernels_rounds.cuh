@@ -42,7 +42,7 @@ struct __align__(8) PromptState {        // walk state carried between rounds (o
     uint8_t pad2[2];
 };
 
-constexpr int kMaxParts = 8;              // the sorted batch runs as up to this many independent parts on their own streams
+constexpr int kMaxParts = 16;             // the sorted batch runs as up to this many independent parts on their own streams
 
 struct RoundBufs {
     uint32_t* act[2];                    // live prompt lists (ping-pong)

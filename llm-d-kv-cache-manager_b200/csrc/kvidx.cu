@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -214,7 +215,7 @@ struct ScoreOut { double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* 
 int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
                         const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
                         int64_t max_blocks) {
-    CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(512));
+    CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(1024));
     CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(PromptState) * 2));
     CK(x->r_nbr.need((size_t)n * 4 * 2)); CK(x->r_role.need((size_t)n * 4)); CK(x->r_hl.need((size_t)n * 4 * 2)); CK(x->r_src.need((size_t)n * 4));
     const int64_t n_al = (n + 63) & ~63ll;
@@ -261,7 +262,7 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         rb[q].grp = rb[q].map + map_slots;
     }
     ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
-    CK(cudaMemsetAsync(x->r_cnt.p, 0, 512, st));
+    CK(cudaMemsetAsync(x->r_cnt.p, 0, 1024, st));
     CK(x->r_fp.need((size_t)n * 8 * 2 + (size_t)n * 4));
     uint64_t* fp_in = x->r_fp.as<uint64_t>(); uint64_t* fp_out = fp_in + n;
     uint32_t* idx_in = reinterpret_cast<uint32_t*>(fp_out + n);
@@ -296,6 +297,7 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         for (int q = 1; q < np; ++q) CK(cudaStreamWaitEvent(strm[q], x->ev_fork, 0));
     }
     const int per_sm = np == 1 ? 4 : 2;
+    const auto t_enq = std::chrono::steady_clock::now();
     for (int64_t r = 0; r < rounds; ++r) {
         const int cur = (int)(r & 1);
         for (int q = 0; q < np; ++q) {
@@ -319,7 +321,7 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
                 finish_round_kernel<16><<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_walk == 1, x->rounds_dedup >= 2, x->rounds_trace);
             }
             x->launches += 5;
-            if (x->rounds_trace) {      // debugging aid: list sizes of this round (synchronises)
+            if (x->rounds_trace == 1) {      // debugging aid: list sizes of this round (synchronises)
                 unsigned int c[8];
                 CK(cudaMemcpyAsync(c, rb[q].n_act, sizeof c, cudaMemcpyDeviceToHost, strm[q]));
                 CK(cudaStreamSynchronize(strm[q]));
@@ -328,6 +330,8 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
             }
         }
     }
+    if (x->rounds_trace == 2) fprintf(stderr, "[kvidx rounds] host enqueue of %lld rounds x %d parts: %.3f ms\n", (long long)rounds, np,
+                                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq).count());
     CK(cudaGetLastError());
     for (int q = 1; q < np; ++q) { CK(cudaEventRecord(x->ev_join[q - 1], strm[q])); CK(cudaStreamWaitEvent(st, x->ev_join[q - 1], 0)); }
     return 0;

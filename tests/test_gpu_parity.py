@@ -404,6 +404,49 @@ def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
     assert np.array_equal(s_t, s_o), np.argwhere(s_t != s_o)[:5]
 
 
+@pytest.mark.parametrize("kernel", ["rounds2", "classes", "classes8", "classes-whole", "classes4-lane"])
+def test_prefix_tree_workload(kernel, monkeypatch):
+    """Prompts drawn from a random prefix TREE (conversations forking off shared history at arbitrary token positions,
+    several levels deep), every branch cached on its own pods up to a random depth.  Prompts leave popular prefixes in
+    the middle of a chunk and keep hitting along less popular -- or private -- branches, which drives the class pipeline
+    through partial followers, capped solo walks, unaligned chunk starts and class re-formation.  Bit-exact vs the oracle."""
+    _select_path(monkeypatch, kernel)
+    rng = np.random.default_rng(2024)
+    BS, P = 16, 48
+    ix, co = _index_pair(capacity=1 << 15, max_pods=P)
+    paths = [rng.integers(0, 60000, size=3000, dtype=np.uint32)]
+    for level in range(4):
+        for _ in range(12):
+            parent = paths[int(rng.integers(0, len(paths)))]
+            cut = int(rng.integers(1, len(parent)))                      # any token position, not block aligned
+            paths.append(np.concatenate([parent[:cut], rng.integers(0, 60000, size=int(rng.integers(200, 2500)), dtype=np.uint32)]))
+    for pth in paths:
+        keys = ix.hash_keys(pth, np.array([0, len(pth)], np.int64))[0]
+        if len(keys) == 0:
+            continue
+        for pod in rng.choice(P, size=int(rng.integers(1, 4)), replace=False):
+            nb = int(rng.integers(1, len(keys) + 1))                     # cached up to a random depth on this pod
+            pt = [(int(pod) << 4) | int(rng.integers(0, 2))]
+            eng = (keys[:nb] ^ np.uint64(0xABCD)).astype(np.uint64)
+            assert ix.add(0, eng, keys[:nb], pt) == 0
+            co.add(0, eng, keys[:nb], pt)
+    prompts = []
+    for i in range(9000):
+        pth = paths[int(rng.integers(0, len(paths))) if i % 4 else 0]
+        cut = int(rng.integers(0, len(pth) + 1))
+        tail = rng.integers(0, 60000, size=int(rng.integers(0, 300)), dtype=np.uint32) if i % 3 else np.zeros(0, np.uint32)
+        prompts.append(np.concatenate([pth[:cut], tail]).astype(np.uint32))
+    tok, off = csr(prompts)
+    s_t, h_t = ix.score_batch(tok, off)
+    s_o, h_o, _, _ = co.score_batch(tok, off, n_threads=4)
+    assert np.array_equal(h_t, h_o) and np.array_equal(s_t, s_o), np.argwhere(s_t != s_o)[:5]
+    assert (s_o.max(axis=1) > 100).sum() > 100
+    sp_p, sp_s, sp_c, _ = ix.score_batch_sparse(tok, off)
+    for i in range(0, len(prompts), 211):
+        got = {int(sp_p[i, j]): float(sp_s[i, j]) for j in range(sp_c[i])}
+        assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
+
+
 def test_rebuild_after_tombstones():
     ix = kvidx.Index(capacity=2048, table_slots=4096)
     co = COracle(size=10 ** 6)
