@@ -304,6 +304,7 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         // the way.  kernel G2 turns either into a partial-follower role if nobody follows the prompt itself.
         {
             int mb = 32, mf = 32, db = 0, df = 0;
+            bool xb = false, xf = false;             // the shared prefix is exact: the neighbour itself is a member of the class
             uint32_t rb_ = kRoleSelf, rf_ = kRoleSelf;
 #pragma unroll
             for (int sft = 1; sft <= 8; ++sft) {
@@ -312,13 +313,13 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 const int dp_f = __shfl_sync(0xffffffffu, dprev, sf);                   // dprev[lane + sft]
                 const int an_b = __shfl_sync(0xffffffffu, (int)shared, sb), an_f = __shfl_sync(0xffffffffu, (int)shared, sf);
                 const uint32_t cb = __shfl_sync(0xffffffffu, cand, sb), cf = __shfl_sync(0xffffffffu, cand, sf);
-                if (lane - sft >= 0 && rb_ == kRoleSelf && mb > 0) { mb = min(mb, dp_b); if (an_b && mb > 0) { rb_ = cb; db = mb; } }
-                if (lane + sft <= 31 && rf_ == kRoleSelf && mf > 0) { mf = min(mf, dp_f); if (an_f && mf > 0) { rf_ = cf; df = mf; } }
+                if (lane - sft >= 0 && rb_ == kRoleSelf && mb > 0) { mb = min(mb, dp_b); if (an_b && mb > 0) { rb_ = cb; db = mb; xb = sft == 1; } }
+                if (lane + sft <= 31 && rf_ == kRoleSelf && mf > 0) { mf = min(mf, dp_f); if (an_f && mf > 0) { rf_ = cf; df = mf; xf = sft == 1; } }
             }
             if (have) {
-                const bool useb = db >= df;
+                const bool useb = (xb != xf) ? xb : db >= df;           // an exact one first, else the longer one
                 rb.anch[i] = useb ? rb_ : rf_;
-                rb.dmin[i] = (uint8_t)((cls && !shared) ? (useb ? db : df) : 0);
+                rb.dmin[i] = (uint8_t)((cls && !shared) ? ((useb ? db : df) | ((useb ? xb : xf) ? 0x80 : 0)) : 0);
             }
         }
     }
@@ -342,6 +343,7 @@ group_lists_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         uint32_t target = kRoleSelf;
         const uint32_t* tp = a.tok; const uint32_t* rp = a.tok;
         int nbc = 0;                                 // blocks both chunks have
+        int dknown = 0;
         if (have) {
             kind = rb.role[i] == kRoleSelf ? 0 : 1;
             const int nb = (int)(rb.nbr[i] & 63u);
@@ -355,7 +357,8 @@ group_lists_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     allow = srcp != p;
                     if (allow) { const uint32_t rs = rb.lslot[srcp]; const uint32_t g = rb.grp[rs]; target = g != kRoleSelf ? g : rs; }
                 }
-                if (allow && target == kRoleSelf && rb.dmin[i] > 0) target = rb.anch[i];
+                const uint32_t hint = rb.dmin[i];                  // kernel G: shared blocks with a neighbour's class | 0x80 if exact
+                if (allow && target == kRoleSelf && (hint & 0x7fu) > 0) target = rb.anch[i];
                 if (target != kRoleSelf && rb.role[target] != kRoleSelf) target = rb.role[target];   // someone with the same chunk represents it
                 if (target == i) target = kRoleSelf;
                 if (target != kRoleSelf) {
@@ -367,10 +370,12 @@ group_lists_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     tp = a.tok + b + first * BS; rp = a.tok + bl + first * BS;
                     // same walk state, model and filter as the class?  (grp / src: by construction; the neighbour hint: checked by kernel G)
                     if (round > 0 && !(rb.src[pl] == rb.src[p] && rb.hstate[pl] == rb.hstate[p])) nbc = 0;
+                    // kernel G compared this prompt with a member of exactly this class already: no need to read the chunks again
+                    if (nbc > 0 && (hint & 0x80u) && rb.anch[i] == target) { dknown = min((int)(hint & 0x7fu), nbc); nbc = 0; }
                 }
             }
         }
-        int dshare = 0;
+        int dshare = dknown;
         uint32_t wm = __ballot_sync(0xffffffffu, nbc > 0);
         while (wm) {
             const int l = __ffs(wm) - 1; wm &= wm - 1;

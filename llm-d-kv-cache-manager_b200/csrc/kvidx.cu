@@ -273,10 +273,10 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
     CK(cudaGetLastError());
     if (x->sort_prefix) {
         size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 32, 64, st));
         CK(x->r_sort.need(tmp));
-        CK(cub::DeviceRadixSort::SortPairs(x->r_sort.p, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
-        x->launches += 6;     // cub: histogram + onesweep passes
+        CK(cub::DeviceRadixSort::SortPairs(x->r_sort.p, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 32, 64, st));
+        x->launches += 5;     // cub: histogram + 4 onesweep passes (the top 32 fingerprint bits order the groups well enough)
     }
     if (max_blocks < 0) {
         unsigned long long mb = 0;
@@ -367,10 +367,10 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
     CK(cudaGetLastError());
     if (x->sort_prefix) {
         size_t tmp = 0;
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 32, 64, st));
         CK(x->r_sort.need(tmp));
-        CK(cub::DeviceRadixSort::SortPairs(x->r_sort.p, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 0, 64, st));
-        x->launches += 6;     // cub: histogram + onesweep passes
+        CK(cub::DeviceRadixSort::SortPairs(x->r_sort.p, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 32, 64, st));
+        x->launches += 5;     // cub: histogram + 4 onesweep passes (the top 32 fingerprint bits order the groups well enough)
     }
     if (max_blocks < 0) {
         unsigned long long mb = 0;
