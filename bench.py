@@ -254,7 +254,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     wl = synth.Workload(CONFIG_ID, T_TOKENS, N_BLOCKS, N_PODS, BLOCK)
-    Q = int(os.environ.get("KVIDX_BENCH_BATCH", str(524288)))      # prompts resident in HBM per step (per GPU)
+    Q = int(os.environ.get("KVIDX_BENCH_BATCH", str(1048576)))      # prompts resident in HBM per step (per GPU)
     QE = int(os.environ.get("KVIDX_BENCH_E2E_BATCH", str(65536)))  # prompts per e2e step (host buffers)
 
     # ---- index: filled through the write path (BlockStored events) ----
@@ -341,18 +341,22 @@ def run_ours(args):
         total_ms = float(tt.item())
     value = world * Q * args.steps / (total_ms / 1e3)
 
-    # the SURVEY's "64K batch" regime on the same resident data (fewer chains in flight, less prefix sharing per batch)
-    q64 = min(Q, 65536)
-    def step64():
-        ix.score_batch_dev(d_tok.data_ptr(), d_off.data_ptr(), q64, d_scores.data_ptr(), d_has_keys=d_has.data_ptr())
-    for _ in range(3):
-        step64()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(); e0.record(stream)
-    for _ in range(5):
-        step64()
-    e1.record(stream); barrier()
-    value_64k = world * q64 * 5 / (e0.elapsed_time(e1) / 1e3)
+    # smaller batches on the same resident data (fewer chains in flight, less prefix sharing per batch): the SURVEY's
+    # "64K batch" regime and half a million prompts
+    def sub_batch(qs):
+        qs = min(Q, qs)
+        def stp():
+            ix.score_batch_dev(d_tok.data_ptr(), d_off.data_ptr(), qs, d_scores.data_ptr(), d_has_keys=d_has.data_ptr())
+        for _ in range(3):
+            stp()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record(stream)
+        for _ in range(5):
+            stp()
+        e1.record(stream); barrier()
+        return world * qs * 5 / (e0.elapsed_time(e1) / 1e3)
+    value_64k = sub_batch(65536)
+    value_512k = sub_batch(524288)
 
     # roofline of the dominant (only) kernel in the step
     A = algorithmic_bytes(wl, m)
@@ -368,8 +372,9 @@ def run_ours(args):
                       "achieved = step's algorithmic bytes / step GPU time (CUDA events around all of its launches), i.e. a lower bound for "
                       "every kernel in it; group_round_kernel (token streaming, 31 % of the step) alone runs at 69 % of DRAM peak (profiles/)",
             "note": "the step is a chain of 9 rounds whose kernels are latency bound at this batch size (serial FNV-1a chain of the "
-                    "representatives: 2.4 us per block; dependent index loads); the fixed cost is ~1.6 ms per step, the marginal cost "
-                    "1.9 ms per 524288 prompts; see DESIGN.md"}
+                    "representatives: 1.5-2.4 us per block; dependent index loads): ~1.75 ms per step whatever the batch size; the "
+                    "marginal cost, ~3 ns per prompt, is the DRAM time of the step's measured traffic (%s KB per prompt, ncu); see DESIGN.md"
+                    % ("%.1f" % (traffic / 1e3) if traffic else "n/a")}
 
     # ---- e2e: host pinned buffers through kvidx_score_batch (H2D + kernel + D2H inside the timed region) ----
     ix.set_stream(0)
@@ -438,7 +443,7 @@ def run_ours(args):
                           "multi_gpu": {"single": "single GPU", "replicas": "replicas: full index per GPU, prompts sharded, no data-path collective",
                                         "sharded": "hash-range sharded tables, probes over NVLink peer memory (CUDA IPC), per-pod ingest ranks"}[mode],
                           "index_fill_s": fill_s, "fill_events": n_ev},
-               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k,
+               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k, "value_at_512k_batch": value_512k,
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         emit(out)
     if world > 1:

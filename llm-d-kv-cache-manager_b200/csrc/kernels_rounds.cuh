@@ -117,11 +117,15 @@ __device__ __forceinline__ void chunk_load(const uint32_t* sp, int nw, int lane,
     }
 }
 
-constexpr int kGroupRing = 4;            // chunks of shared memory per warp: one being compared, its predecessor, two in flight
+#ifndef KVX_GROUP_RING
+#define KVX_GROUP_RING 4
+#define KVX_GROUP_MINB 3
+#endif
+constexpr int kGroupRing = KVX_GROUP_RING;            // chunks of shared memory per warp: one being compared, its predecessor, two in flight
 struct GroupSmem { uint4 ring[kGroupThreads / 32][kGroupRing][4][32]; };     // 64 KB
 
 template <int BS>
-__global__ void __launch_bounds__(kGroupThreads, 3)
+__global__ void __launch_bounds__(kGroupThreads, KVX_GROUP_MINB)
 group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int dedup) {
     static_assert(BS == 16 && kRoundBlocks == 32, "a chunk is 4 x 32 lanes x 16 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw_g[];
@@ -895,16 +899,17 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
 // Lane per follower.  Representative continues: so does the follower, with the representative's chain state, and its
 // walk state stays where the representative left it (src).  Representative finished: same pods, same scores -- the warp
 // writes the follower's result from the representative's final state.
-__device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int reps_too) {
+__device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int reps_too,
+                                              const unsigned int bid, const unsigned int nbl) {
     const int lane = threadIdx.x & 31;
     {   // kernel P is done with need_snap: clear it for the next round
         uint32_t* f4 = reinterpret_cast<uint32_t*>(rb.need_snap);
-        for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < rb.part_size / 4; x += (size_t)gridDim.x * blockDim.x) f4[x] = 0u;
+        for (size_t x = bid * (size_t)blockDim.x + threadIdx.x; x < rb.part_size / 4; x += (size_t)nbl * blockDim.x) f4[x] = 0u;
     }
     if (reps_too) {                                            // representatives that continue (walk_round_kernel leaves the list to us)
         const unsigned int n_a = rb.n_hl[0];
-        const unsigned int tw = gridDim.x * (blockDim.x / 32);
-        for (unsigned int w = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_a; w += tw) {
+        const unsigned int tw = nbl * (blockDim.x / 32);
+        for (unsigned int w = bid * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_a; w += tw) {
             const unsigned int i = w * 32u + lane;
             const unsigned int li = i < n_a ? rb.hl[i] : 0u;
             const bool more = i < n_a && rb.fate[li] == kFateMore;
@@ -918,8 +923,8 @@ __device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArg
     }
     const unsigned int n_fl = rb.n_hl[1];
     const PromptState* pst_cur = rb.pst[round & 1];
-    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
-    for (unsigned int w = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_fl; w += total_warps) {
+    const unsigned int total_warps = nbl * (blockDim.x / 32);
+    for (unsigned int w = bid * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_fl; w += total_warps) {
         const unsigned int f = w * 32u + lane;
         const bool have = f < n_fl;
         uint32_t p = 0, pl = 0; uint8_t ft = 0;
@@ -987,15 +992,16 @@ __device__ __forceinline__ uint64_t hash_block16(uint64_t parent, const uint32_t
 constexpr int kDetachBlocks = 3;          // blocks a partial follower walks alone inside the round before it is re-queued
 struct DetachSmem { double sc[256 / 32][kMaxEnt][32]; uint16_t pod[256 / 32][kMaxEnt][32]; };
 template <int BS>
-__device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int trace, DetachSmem& sm) {
+__device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int trace, DetachSmem& sm,
+                                             const unsigned int bid, const unsigned int nbl) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned int n_dl = rb.n_hl[2];
     const PromptState* pst_rd = rb.pst[round & 1];
     PromptState* pst_cur = rb.pst[round & 1];
     const size_t kstride = (size_t)a.n_prompts;
     const bool peer = t.shard_bits != 0;
-    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
-    for (unsigned int w = blockIdx.x * (blockDim.x / 32) + wid; w * 32u < n_dl; w += total_warps) {
+    const unsigned int total_warps = nbl * (blockDim.x / 32);
+    for (unsigned int w = bid * (blockDim.x / 32) + wid; w * 32u < n_dl; w += total_warps) {
         const unsigned int f = w * 32u + lane;
         const bool have = f < n_dl;
         uint32_t p = 0, meta = 0;
@@ -1115,8 +1121,12 @@ template <int BS>
 __global__ void __launch_bounds__(256)
 finish_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int reps_too, const int detach, const int trace) {
     __shared__ DetachSmem sm;
-    resolve_round(t, a, rb, cur, round, reps_too);
-    if (detach) detach_round<BS>(t, a, rb, cur, round, trace, sm);
+    if (!detach) { resolve_round(t, a, rb, cur, round, reps_too, blockIdx.x, gridDim.x); return; }
+    // odd CTAs take the followers, even CTAs the partial followers: the two latency chains run side by side
+    const unsigned int half = gridDim.x / 2;
+    if (gridDim.x < 2) { resolve_round(t, a, rb, cur, round, reps_too, 0, 1); detach_round<BS>(t, a, rb, cur, round, trace, sm, 0, 1); }
+    else if (blockIdx.x & 1) { if (blockIdx.x / 2 < half) resolve_round(t, a, rb, cur, round, reps_too, blockIdx.x / 2, half); }
+    else detach_round<BS>(t, a, rb, cur, round, trace, sm, blockIdx.x / 2, (gridDim.x + 1) / 2);
 }
 
 // List setup + a 64-bit fingerprint of every prompt's first block.  The batch is then radix-sorted by fingerprint so
