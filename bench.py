@@ -265,11 +265,11 @@ def run_ours(args):
     from kvidx import dist as kd
     mode = os.environ.get("KVIDX_BENCH_MODE", "replicas") if world > 1 else "single"
     if mode == "sharded":
-        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + 1024 * world, max_pods=wl.P, tier_weights=WEIGHTS, device=local,
+        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + (1 << 20), max_pods=wl.P, tier_weights=WEIGHTS, device=local,
                          shard_rank=rank, shard_count=world)
         kd.connect_shards(ix, dev)
     else:
-        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + 1024, max_pods=wl.P, tier_weights=WEIGHTS, device=local)
+        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + (1 << 20), max_pods=wl.P, tier_weights=WEIGHTS, device=local)
     t0 = time.time()
     n_ev = 0
     for d0 in range(0, wl.D, 4096):
@@ -358,6 +358,43 @@ def run_ours(args):
     value_64k = sub_batch(65536)
     value_512k = sub_batch(524288)
 
+    # ---- SURVEY config #5: Score() with the write path running beside it (100 K events/s: BlockStored of new documents,
+    # BlockRemoved of the ones stored one step earlier; same handle, host arrays, calls interleaved per step) ----
+    mixed = None
+    if not os.environ.get("KVIDX_BENCH_SKIP_MIXED"):
+        step_s = (total_ms / args.steps) / 1e3
+        ev_per_step = max(16, int(100000 * step_s * 2.2))             # the interleaved step is ~2x longer than the score step alone
+        docs_per_step = max(1, ev_per_step // 20)                       # ~10 stored + ~10 removed events per document
+        n_mixed = 8
+        churn0 = wl.D                                                   # documents beyond the indexed ones
+        batches = []
+        for s_i in range(n_mixed + 1):
+            ev, hs, tk = wl.fill_events(churn0 + s_i * docs_per_step, churn0 + (s_i + 1) * docs_per_step)
+            if mode == "sharded":
+                ev = kd.events_for_rank(ev, rank, world)
+            rm = ev.copy(); rm["op"] = 1; rm["has_parent"] = 0; rm["n_tokens"] = 0
+            batches.append((ev, rm, hs, tk))
+        n_events = 0
+        torch.cuda.synchronize(); barrier()
+        t0 = time.perf_counter()
+        for s_i in range(1, n_mixed + 1):
+            ev, _, hs, tk = batches[s_i]
+            rc, dropped = ix.apply_events(ev, hs, tk); assert rc == 0 and dropped == 0
+            _, rm, hs0, tk0 = batches[s_i - 1]
+            if s_i > 1:
+                rc, dropped = ix.apply_events(rm, hs0, tk0); assert rc == 0
+                n_events += len(rm)
+            n_events += len(ev)
+            step_dev()
+        torch.cuda.synchronize(); barrier()
+        dt = time.perf_counter() - t0
+        assert nocheck or np.array_equal(d_scores[:4096].cpu().numpy(), exp), "score mismatch with the write path running"
+        mixed = {"score_prompts_per_s": world * Q * n_mixed / dt, "events_per_s": world * n_events / dt, "blocks_per_event": wl.bpe,
+                 "note": "wall clock over %d steps of [apply_events(stored), apply_events(removed), score]; scores of the resident batch "
+                         "stay bit-exact" % n_mixed}
+        # leave the index as it was: remove the last stored batch
+        ix.apply_events(batches[n_mixed][1], batches[n_mixed][2], batches[n_mixed][3])
+
     # roofline of the dominant (only) kernel in the step
     A = algorithmic_bytes(wl, m)
     peak, peak_src = measured_peak()
@@ -443,7 +480,7 @@ def run_ours(args):
                           "multi_gpu": {"single": "single GPU", "replicas": "replicas: full index per GPU, prompts sharded, no data-path collective",
                                         "sharded": "hash-range sharded tables, probes over NVLink peer memory (CUDA IPC), per-pod ingest ranks"}[mode],
                           "index_fill_s": fill_s, "fill_events": n_ev},
-               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k, "value_at_512k_batch": value_512k,
+               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k, "value_at_512k_batch": value_512k, "mixed_read_write": mixed,
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         emit(out)
     if world > 1:

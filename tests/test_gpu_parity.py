@@ -318,6 +318,23 @@ def test_synth_config2_shape_vs_oracle_and_closed_form(kernel, monkeypatch):
     assert np.array_equal(s1, wl.expected_scores(doc, m))
 
 
+@pytest.mark.parametrize("kernel", ["fused", "rounds2", "classes", "classes8"])
+def test_synth_config3_shape_long_prompts(kernel, monkeypatch):
+    """BASELINE config #3 shape at reduced N: 8192-token prompts (512 blocks = 16 rounds), 256 pods."""
+    _select_path(monkeypatch, kernel)
+    wl = synth.Workload(3, 8192, 1 << 16, 256)
+    ix, co = _index_pair(capacity=1 << 17, max_pods=256)
+    ev, hs, tk = wl.fill_events(0, wl.D)
+    assert ix.apply_events(ev, hs, tk) == (0, 0) and co.apply_events(ev, hs, tk) == (0, 0)
+    toks, doc, m = wl.queries(0, 700)
+    off = np.arange(0, (len(toks) + 1) * wl.T, wl.T, dtype=np.int64)
+    s1, h1 = ix.score_batch(toks.reshape(-1), off)
+    s2, h2, _, _ = co.score_batch(toks.reshape(-1), off, n_threads=4)
+    assert np.array_equal(s1, s2) and h1.all()
+    assert np.array_equal(s1, wl.expected_scores(doc, m))
+    assert m.max() > 480                                   # some walks go through (nearly) all 16 rounds
+
+
 @pytest.mark.parametrize("kernel", ["fused"] + ROUND_PATHS)
 def test_tuned_kernel_ragged_misaligned_and_many_prompts(kernel, monkeypatch):
     """Lane refill / round lists, unaligned prompt starts (per-lane staging fallback), empty and sub-block
@@ -445,6 +462,57 @@ def test_prefix_tree_workload(kernel, monkeypatch):
     for i in range(0, len(prompts), 211):
         got = {int(sp_p[i, j]): float(sp_s[i, j]) for j in range(sp_c[i])}
         assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
+
+
+def test_config5_scores_while_the_write_path_runs():
+    """BASELINE config #5 in miniature: one thread keeps storing and removing documents through apply_events while another
+    scores prompts of documents the writer never touches.  Calls on one handle serialise, so every Score() sees the index
+    between two event batches; the untouched documents' scores must be exact in every call, and the final index must equal
+    the oracle's after the same event sequence."""
+    import threading
+    wl = synth.Workload(5, 1024, 1 << 14, 32)
+    ix, co = _index_pair(capacity=1 << 16, max_pods=32)
+    ev, hs, tk = wl.fill_events(0, wl.D)
+    assert ix.apply_events(ev, hs, tk) == (0, 0) and co.apply_events(ev, hs, tk) == (0, 0)
+    toks, doc, m = wl.queries(0, 3000)
+    off = np.arange(0, (len(toks) + 1) * wl.T, wl.T, dtype=np.int64)
+    want = wl.expected_scores(doc, m)
+    churn = []
+    for s_i in range(12):
+        e, h, t = wl.fill_events(wl.D + 8 * s_i, wl.D + 8 * (s_i + 1))
+        r = e.copy(); r["op"] = 1; r["has_parent"] = 0; r["n_tokens"] = 0
+        churn.append((e, r, h, t))
+    errs = []
+
+    def writer():
+        try:
+            for i, (e, r, h, t) in enumerate(churn):
+                assert ix.apply_events(e, h, t) == (0, 0)
+                if i % 3 != 2:                              # every third batch stays
+                    assert ix.apply_events(r, h, t)[0] == 0
+        except Exception as ex:                             # noqa: BLE001
+            errs.append(ex)
+
+    th = threading.Thread(target=writer)
+    th.start()
+    for _ in range(6):
+        s1, _ = ix.score_batch(toks.reshape(-1), off)
+        if not np.array_equal(s1, want):
+            errs.append(AssertionError("scores changed while events were applied"))
+    th.join()
+    assert not errs, errs[:1]
+    for i, (e, r, h, t) in enumerate(churn):
+        co.apply_events(e, h, t)
+        if i % 3 != 2:
+            co.apply_events(r, h, t)
+    assert ix.stats()["request_keys"] == co.len_request()
+    q2, d2, m2 = wl.queries(5000, 5400)
+    kept = np.concatenate([wl.doc_tokens(wl.D + 8 * i, wl.D + 8 * (i + 1)) for i in range(12) if i % 3 == 2])
+    tok2 = np.concatenate([q2.reshape(-1), kept.reshape(-1)])
+    off2 = np.arange(0, (len(q2) + len(kept) + 1) * wl.T, wl.T, dtype=np.int64)
+    a, _ = ix.score_batch(tok2, off2)
+    b, _, _, _ = co.score_batch(tok2, off2, n_threads=4)
+    assert np.array_equal(a, b) and (b[len(q2):].max(axis=1) > 0).all()
 
 
 def test_rebuild_after_tombstones():
