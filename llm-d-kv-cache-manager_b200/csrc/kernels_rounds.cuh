@@ -155,33 +155,21 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             if (a.model) mdl = a.model[p];
         }
         const bool cls = have && nb > 0 && dedup;
-        // Does the prompt equal its predecessor in the list?  (The list is sorted by prefix, so mostly yes.)  Everything
-        // but the tokens lane-parallel here; the tokens as the chunks stream by below.
         uint64_t fsum = 0;
         if (cls && round == 0 && a.filter) { const uint64_t* fr = a.filter + (int64_t)p * t.filter_words; for (uint32_t x = 0; x < t.filter_words; ++x) fsum = (fsum ^ fr[x]) * 0x9E3779B97F4A7C15ull; }
-        bool eqm, eqf;                               // compatible with the predecessor for sharing a chunk prefix / a whole chunk
-        const int nb_up = __shfl_up_sync(0xffffffffu, nb, 1);
-        {
-            const int more_u = __shfl_up_sync(0xffffffffu, (int)more, 1);
-            const uint32_t mdl_u = __shfl_up_sync(0xffffffffu, mdl, 1), src_u = __shfl_up_sync(0xffffffffu, srcp, 1);
-            const uint64_t h_u = __shfl_up_sync(0xffffffffu, hprev, 1), f_u = __shfl_up_sync(0xffffffffu, fsum, 1);
-            const int cls_u = __shfl_up_sync(0xffffffffu, (int)cls, 1);
-            eqm = cls && lane > 0 && cls_u && mdl_u == mdl && src_u == srcp && h_u == hprev && f_u == fsum;
-            if (eqm && round == 0 && a.filter) {       // equal filter fingerprints: compare the rows themselves
-                const uint32_t pu = rb.act[cur][i - 1];
-                const uint64_t* fa = a.filter + (int64_t)p * t.filter_words; const uint64_t* fb = a.filter + (int64_t)pu * t.filter_words;
-                for (uint32_t x = 0; x < t.filter_words; ++x) eqm = eqm && fa[x] == fb[x];
-            }
-            eqf = eqm && nb_up == nb && more_u == (int)more;
-        }
-        // chunks, one prompt at a time: each is compared with its predecessor's (still in the ring) and -- only if it
-        // differs -- folded into a fingerprint for the election
+        // The chunks stream through a 3-slot ring (one being examined, two in flight); a fourth slot keeps the ANCHOR: the chunk
+        // of the class the list is currently running through (the list is sorted by prefix, so class-mates are neighbours).
+        // A chunk equal to the anchor (and with the same walk state, model, filter, length) is a member of the anchor's
+        // class: nothing else to do for it.  A chunk that starts like the anchor but differs is a prompt leaving that class
+        // inside the chunk: it goes through the election like any new chunk, and remembers (class, shared blocks) as an exact
+        // hint for kernel G2.  A chunk unrelated to the anchor -- or one that differs from an anchor nobody has joined yet --
+        // becomes the anchor.
         uint32_t f0 = 0, f1 = 0;
-        bool eqprev = false;                         // same class as the previous list entry
-        int dprev = 0;                               // leading blocks of the chunk equal to the previous list entry's
+        bool eqanch = false;                          // member of the class of lane `alane`
+        int alane = -1;
+        int dh = 0, hlane = -1;                       // hint: shares dh leading blocks with the chunk of lane hlane
+        int anchor = -1, members = 0;                 // warp-uniform: the anchor's lane, prompts that matched it so far
         uint32_t todo = __ballot_sync(0xffffffffu, cls);
-        const uint32_t eqm_mask = __ballot_sync(0xffffffffu, eqm), eqf_mask = __ballot_sync(0xffffffffu, eqf);
-        // chunk q of the list lands in ring slot (its ordinal % kGroupRing) through cp.async; two chunks stay in flight
         auto issue = [&](int slot, int qi) {
             if (qi >= 0) {
                 const uint32_t* sp = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, qi));
@@ -199,42 +187,59 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             }
             cp_async_commit();
         };
-        constexpr int PD = kGroupRing - 2;
+        constexpr int RS = kGroupRing - 1;            // rotating slots; slot RS holds the anchor
+        constexpr int PD = RS - 1;                    // chunks in flight
         uint32_t pend = todo;
         int issued = 0;
 #pragma unroll
         for (int u = 0; u < PD; ++u) {
             const int qi = pend ? __ffs(pend) - 1 : -1;
             pend &= pend - 1;
-            issue(issued % kGroupRing, qi); ++issued;
+            issue(issued % RS, qi); ++issued;
         }
-        int qprev = -2, ord = 0;
+        int ord = 0;
         while (todo) {
             const int q = __ffs(todo) - 1;
             todo &= todo - 1;
             {
                 const int qi = pend ? __ffs(pend) - 1 : -1;
                 pend &= pend - 1;
-                issue(issued % kGroupRing, qi); ++issued;
+                issue(issued % RS, qi); ++issued;
             }
             cp_async_wait<PD>();
             uint4 v[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) v[c] = ring[ord % kGroupRing][c][lane];
-            bool same = false;
-            if (qprev == q - 1 && ((eqm_mask >> q) & 1u)) {          // warp-uniform
-                int fb = 32;                                          // first block in which this lane's pieces differ
-#pragma unroll
-                for (int c = 3; c >= 0; --c) {
-                    const uint4 u = ring[(ord + kGroupRing - 1) % kGroupRing][c][lane];
-                    if (((v[c].x ^ u.x) | (v[c].y ^ u.y) | (v[c].z ^ u.z) | (v[c].w ^ u.w)) != 0u) fb = c * 8 + (lane >> 2);
+            for (int c = 0; c < 4; ++c) v[c] = ring[ord % RS][c][lane];
+            bool same = false, compat = false;
+            int fbc = 0;
+            if (anchor >= 0) {
+                const int nb_q = __shfl_sync(0xffffffffu, nb, q), nb_a = __shfl_sync(0xffffffffu, nb, anchor);
+                compat = __shfl_sync(0xffffffffu, mdl, q) == __shfl_sync(0xffffffffu, mdl, anchor) &&
+                         __shfl_sync(0xffffffffu, srcp, q) == __shfl_sync(0xffffffffu, srcp, anchor) &&
+                         __shfl_sync(0xffffffffu, hprev, q) == __shfl_sync(0xffffffffu, hprev, anchor) &&
+                         __shfl_sync(0xffffffffu, fsum, q) == __shfl_sync(0xffffffffu, fsum, anchor);
+                if (compat && round == 0 && a.filter) {           // equal filter fingerprints: compare the rows themselves
+                    const uint32_t pq = __shfl_sync(0xffffffffu, p, q), pa = __shfl_sync(0xffffffffu, p, anchor);
+                    bool eqr = true;
+                    for (uint32_t x = lane; x < t.filter_words; x += 32) eqr = eqr && a.filter[(int64_t)pq * t.filter_words + x] == a.filter[(int64_t)pa * t.filter_words + x];
+                    compat = __all_sync(0xffffffffu, eqr);
                 }
-                fb = __reduce_min_sync(0xffffffffu, fb);
-                same = fb == 32 && ((eqf_mask >> q) & 1u);
-                if (lane == q) dprev = min(fb, min(nb, nb_up));
+                if (compat) {
+                    int fb = 32;                                  // first block in which this lane's pieces differ
+#pragma unroll
+                    for (int c = 3; c >= 0; --c) {
+                        const uint4 u = ring[RS][c][lane];
+                        if (((v[c].x ^ u.x) | (v[c].y ^ u.y) | (v[c].z ^ u.z) | (v[c].w ^ u.w)) != 0u) fb = c * 8 + (lane >> 2);
+                    }
+                    fb = __reduce_min_sync(0xffffffffu, fb);
+                    fbc = min(fb, min(nb_q, nb_a));
+                    same = fb == 32 && nb_q == nb_a && __shfl_sync(0xffffffffu, (int)more, q) == __shfl_sync(0xffffffffu, (int)more, anchor);
+                }
             }
-            if (same) { if (lane == q) eqprev = true; }
-            else {
+            if (same) {
+                if (lane == q) { eqanch = true; alane = anchor; }
+                ++members;
+            } else {
                 uint32_t a0 = 0, a1 = 0;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
@@ -246,13 +251,23 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 a0 = __reduce_xor_sync(0xffffffffu, a0);
                 a1 = __reduce_xor_sync(0xffffffffu, a1);
                 if (lane == q) { f0 = a0; f1 = a1; }
+                bool take = true;                                // does this chunk become the anchor?
+                if (anchor >= 0 && compat && fbc >= 1) {
+                    if (members > 0) { take = false; if (lane == q) { dh = fbc; hlane = anchor; } }      // leaves the anchor's class
+                    else if (lane == anchor) { dh = fbc; hlane = q; }                                      // ... or the old anchor leaves this one's
+                }
+                if (take) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) ring[RS][c][lane] = v[c];
+                    anchor = q; members = 0;
+                }
             }
-            qprev = q; ++ord;
+            ++ord;
         }
         cp_async_wait<0>();
-        // election among the prompts that differ from their predecessor
+        // election among the prompts that are not members of an anchor's class
         uint32_t cand = kRoleSelf;
-        if (cls && !eqprev) {
+        if (cls && !eqanch) {
             const uint64_t key = mix64((((uint64_t)f1 << 32) | f0) ^ (hprev * 0xFF51AFD7ED558CCDull) ^ ((uint64_t)srcp << 17) ^ (uint64_t)(nb | (more ? 64 : 0)) ^
                                        ((uint64_t)mdl * 0xC2B2AE3D27D4EB4Full) ^ fsum);
             cand = atomicCAS(&rb.map[(uint32_t)key & rb.map_mask], kRoleSelf, i);
@@ -290,40 +305,27 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             const bool same = __all_sync(0xffffffffu, d == 0u);
             if (lane == l) shared = same;
         }
-        // a prompt equal to its predecessor takes the class of the nearest preceding prompt that went through the election
+        // members take the outcome of their anchor (which went through the election); hints are resolved the same way
         {
-            const uint32_t heads = ~__ballot_sync(0xffffffffu, eqprev);            // lane 0 is always a head
-            const int hd = 31 - __clz(heads & ((2u << lane) - 1u));
-            const uint32_t cand_h = __shfl_sync(0xffffffffu, cand, hd);
-            const int shared_h = __shfl_sync(0xffffffffu, (int)shared, hd);
-            const unsigned int i_h = __shfl_sync(0xffffffffu, i, hd);
-            if (eqprev) { shared = true; cand = shared_h ? cand_h : i_h; }
+            const int al_ = eqanch ? alane : lane;
+            const uint32_t cand_h = __shfl_sync(0xffffffffu, cand, al_);
+            const int shared_h = __shfl_sync(0xffffffffu, (int)shared, al_);
+            const unsigned int i_h = __shfl_sync(0xffffffffu, i, al_);
+            if (eqanch) { shared = true; cand = shared_h ? cand_h : i_h; }
         }
         if (have) { rb.role[i] = shared ? cand : kRoleSelf; if (shared) rb.nfol[cand] = 1; }
         // Every member of a class tells the prompts that shared its state last round (same src) where the class lives:
-        // kernel G2 compares the ones that stayed alone with this class's chunk.
+        // kernel G2 points the ones that stayed alone at this class.
         if (shared && round > 0) rb.grp[rb.lslot[srcp]] = cand;
-        // A prompt that stayed alone may also start like a neighbouring class: walk the list (<= 8 entries each way) to the nearest
-        // member of a class; the chunk prefix shared with it is at least the minimum of the pairwise shared prefixes on
-        // the way.  kernel G2 turns either into a partial-follower role if nobody follows the prompt itself.
         {
-            int mb = 32, mf = 32, db = 0, df = 0;
-            bool xb = false, xf = false;             // the shared prefix is exact: the neighbour itself is a member of the class
-            uint32_t rb_ = kRoleSelf, rf_ = kRoleSelf;
-#pragma unroll
-            for (int sft = 1; sft <= 8; ++sft) {
-                const int sb = max(lane - sft, 0), sf = min(lane + sft, 31);
-                const int dp_b = __shfl_sync(0xffffffffu, dprev, min(sb + 1, 31));      // dprev[lane - sft + 1]
-                const int dp_f = __shfl_sync(0xffffffffu, dprev, sf);                   // dprev[lane + sft]
-                const int an_b = __shfl_sync(0xffffffffu, (int)shared, sb), an_f = __shfl_sync(0xffffffffu, (int)shared, sf);
-                const uint32_t cb = __shfl_sync(0xffffffffu, cand, sb), cf = __shfl_sync(0xffffffffu, cand, sf);
-                if (lane - sft >= 0 && rb_ == kRoleSelf && mb > 0) { mb = min(mb, dp_b); if (an_b && mb > 0) { rb_ = cb; db = mb; xb = sft == 1; } }
-                if (lane + sft <= 31 && rf_ == kRoleSelf && mf > 0) { mf = min(mf, dp_f); if (an_f && mf > 0) { rf_ = cf; df = mf; xf = sft == 1; } }
-            }
+            const int hl_ = hlane >= 0 ? hlane : lane;
+            const uint32_t cand_h = __shfl_sync(0xffffffffu, cand, hl_);
+            const int shared_h = __shfl_sync(0xffffffffu, (int)shared, hl_);
+            const unsigned int i_h = __shfl_sync(0xffffffffu, i, hl_);
             if (have) {
-                const bool useb = (xb != xf) ? xb : db >= df;           // an exact one first, else the longer one
-                rb.anch[i] = useb ? rb_ : rf_;
-                rb.dmin[i] = (uint8_t)((cls && !shared) ? ((useb ? db : df) | ((useb ? xb : xf) ? 0x80 : 0)) : 0);
+                const bool hint = cls && !shared && hlane >= 0 && dh > 0;
+                rb.anch[i] = hint ? (shared_h ? cand_h : i_h) : kRoleSelf;
+                rb.dmin[i] = (uint8_t)(hint ? (dh | 0x80) : 0);     // exact: measured against a chunk of that very class
             }
         }
     }
@@ -362,7 +364,8 @@ group_lists_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     if (allow) { const uint32_t rs = rb.lslot[srcp]; const uint32_t g = rb.grp[rs]; target = g != kRoleSelf ? g : rs; }
                 }
                 const uint32_t hint = rb.dmin[i];                  // kernel G: shared blocks with a neighbour's class | 0x80 if exact
-                if (allow && target == kRoleSelf && (hint & 0x7fu) > 0) target = rb.anch[i];
+                // a hinted class is only safe to lean on if it has followers (then its representative stays one)
+                if (allow && target == kRoleSelf && (hint & 0x7fu) > 0 && rb.anch[i] != kRoleSelf && rb.nfol[rb.anch[i]]) target = rb.anch[i];
                 if (target != kRoleSelf && rb.role[target] != kRoleSelf) target = rb.role[target];   // someone with the same chunk represents it
                 if (target == i) target = kRoleSelf;
                 if (target != kRoleSelf) {
