@@ -1,24 +1,26 @@
-// kernels_rounds.cuh -- Score() for LARGE batches as alternating rounds of two specialised kernels.
+// kernels_rounds.cuh -- Score() for LARGE batches: rounds over PREFIX CLASSES.
 //
-// Same reference path as kernels_score.cuh (GetPodScores steps 2-4, pkg/kvcache/indexer.go:141-163);
-// different decomposition.  The fused persistent kernel makes every lane a little state machine (stage,
-// hash, probe, score, retire, refill); ncu showed it stuck at ~0.4 IPC per scheduler with ~20 resident
-// warps/SM, because the state each lane carries (~94 registers + ~300 B shared) caps occupancy while
-// the non-hash phases add serial latency per block.  Here the two halves of the work get the shape
-// each one wants:
+// Same reference path as kernels_score.cuh (GetPodScores steps 2-4, pkg/kvcache/indexer.go:141-163): chain keys
+// (token_processor.go:94-162), Lookup (in_memory.go:105-146), LongestPrefixScorer.Score (kvblock_scorer.go:108-151).
 //
-//   round r, kernel H (hash_round_kernel):  prompts that are still on the consecutive-prefix walk hash
-//       their next kRoundBlocks blocks.  Lockstep, thin lanes (no score / probe state), the branch-free
-//       FNV/CBOR code at the pipe-saturating occupancy measured by scripts/ubench_hash.cu.  Keys go to
-//       a per-round buffer in HBM (8 B per block -- versus 64 B of tokens and 64 B of slot read).
-//   round r, kernel P (probe_round_kernel): one WARP per prompt: the 32 lanes probe the round's 32 keys
-//       at once (32 independent 64-byte reads in flight per warp -> the memory system sees full
-//       parallelism instead of one dependent probe per lane), a ballot finds the first miss, and the
-//       longest-prefix walk + in-order f64 accumulation runs on the hits (lane q owns block-0 pod q).
-//       Prompts whose walk continues are appended to the next round's list.
+// A large batch repeats itself: thousands of prompts share a system prompt or a document, and the per-prompt kernels
+// hash and probe that shared prefix once per prompt.  Here the batch is processed in rounds of kRoundBlocks blocks, and
+// in every round the live prompts are partitioned into CLASSES -- same walk state, same model and filter, and a
+// token-for-token identical next chunk.  One representative per class is hashed and walked; the other members take its
+// outcome.  Class membership is never decided by a hash: every member has been compared with its class's chunk, so the
+// results are bit-identical to the per-prompt kernels and the oracle for any input (tests run all paths).
 //
-// Early termination costs at most one round of extra hashing per prompt.  Results are bit-identical to
-// the fused kernel and the oracle (tests run both paths).
+//   G   group_round_kernel   stream every live prompt's chunk once, find the classes (compare with the running class's
+//                            anchor chunk; election through a small map for the rest)
+//   G2  group_lists_kernel   prompts that leave a class in the middle of the chunk become partial followers (class, d);
+//                            compact the lists: representatives / followers / partial followers
+//   H   hash_round_kernel    FNV-64a / CBOR chain keys of the representatives' chunks
+//   P   walk_round_kernel    warp per representative: 32 probes at once, ordered scoring of the hits, run snapshots
+//   R+D finish_round_kernel  followers copy their representative's fate; partial followers resume from its snapshot and
+//                            walk their own blocks; next round's live list
+//
+// The per-round cost is a fixed ~0.2 ms of short latency-bound kernels (hidden by running the batch as independent parts
+// on separate streams), so medium batches use kernels_rounds_plain.cuh instead (see kvidx.cu: launch_score).
 #pragma once
 #include <cuda_runtime.h>
 #include "kernels_score.cuh"
@@ -27,7 +29,6 @@ namespace kvx {
 
 constexpr int kRoundBlocks = 32;         // blocks hashed per prompt per round (== lanes per warp in kernel P)
 constexpr int kHashThreads = 256;
-constexpr int kProbeThreads = 256;
 constexpr int kGroupThreads = 256;
 constexpr uint32_t kRoleSelf = 0xffffffffu;
 
@@ -117,15 +118,11 @@ __device__ __forceinline__ void chunk_load(const uint32_t* sp, int nw, int lane,
     }
 }
 
-#ifndef KVX_GROUP_RING
-#define KVX_GROUP_RING 4
-#define KVX_GROUP_MINB 3
-#endif
-constexpr int kGroupRing = KVX_GROUP_RING;            // chunks of shared memory per warp: one being compared, its predecessor, two in flight
+constexpr int kGroupRing = 4;            // chunk slots per warp: one being examined, two in flight, the anchor (deeper rings measured: slower)
 struct GroupSmem { uint4 ring[kGroupThreads / 32][kGroupRing][4][32]; };     // 64 KB
 
 template <int BS>
-__global__ void __launch_bounds__(kGroupThreads, KVX_GROUP_MINB)
+__global__ void __launch_bounds__(kGroupThreads, 3)
 group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int dedup) {
     static_assert(BS == 16 && kRoundBlocks == 32, "a chunk is 4 x 32 lanes x 16 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw_g[];
@@ -511,7 +508,7 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
     }
 }
 
-// ---- kernel P ---------------------------------------------------------------------------------
+// ---- helpers shared with kernels_rounds_plain.cuh ---------------------------------------------
 __device__ __forceinline__ void ld_slot_pair(const ReqSlot* s, bool peer, uint4& a0, uint4& b0, uint4& a1, uint4& b1) {
     ld_slot(s, peer, a0, b0);
     ld_slot(s + 1, peer, a1, b1);
@@ -523,213 +520,10 @@ __device__ __forceinline__ uint32_t ent_of(uint32_t e0, uint32_t e1, uint32_t e2
     return (j & 1) ? (word >> 16) : (word & 0xffffu);
 }
 
-// Kernel P, lane-per-prompt.  (Two warp-per-prompt versions came first -- 32 lanes probing a prompt's 32 keys at
-// once, then the same software-pipelined.  Both cost ~700 issue slots per prompt-round because the walk itself
-// runs on <= 10 lanes while the other 22 idle, and stayed at ~25 % issue utilisation: profiles/r1d_*.)  Here a
-// warp walks 32 prompts in lockstep, one block per iteration: every instruction serves 32 prompts, the 32 lanes'
-// probes are 32 independent 64-byte reads, and the slot pair for block j+1 is in flight while block j is scored.
-struct WalkSmem {
-    struct Warp {
-        double sc[kMaxEnt][32];
-        uint16_t pod[kMaxEnt][32];
-        uint8_t bt[kMaxEnt][32];
-    };
-    Warp w[kProbeThreads / 32];
-    double weight[16];
-};
-
-__global__ void __launch_bounds__(kProbeThreads, 4)
-probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
-    extern __shared__ __align__(16) unsigned char smem_raw_w[];
-    WalkSmem& sm = *reinterpret_cast<WalkSmem*>(smem_raw_w);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WalkSmem::Warp& W = sm.w[wid];
-    if (threadIdx.x < 16) sm.weight[threadIdx.x] = t.weight[threadIdx.x];
-    __syncthreads();
-    const unsigned int n_act = rb.n_hl[0];                     // representatives this round
-    const size_t kstride = (size_t)a.n_prompts;
-    const bool peer = t.shard_bits != 0;
-    const PromptState* pst_prev = rb.pst[(round & 1) ^ 1];
-    PromptState* pst_cur = rb.pst[round & 1];
-    const unsigned int total_warps = gridDim.x * (kProbeThreads / 32);
-    for (unsigned int w = blockIdx.x * (kProbeThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
-        const unsigned int i = w * 32u + lane;                 // position in the representative list
-        const bool have = i < n_act;
-        const unsigned int li = have ? rb.hl[i] : 0u;          // its live slot
-        const uint32_t p = have ? rb.act[cur][li] : 0u;
-        const uint32_t meta = have ? rb.nbr[li] : 0u;
-        const int nb = (int)(meta & 63u);
-        const bool has_more = (meta >> 8) & 1u;
-        const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
-        const unsigned int ks = i;
-        const bool snapf = have && rb.need_snap[li];           // partial followers will pick up this walk mid-chunk
-        uint32_t nwalk = 0;
-        uint64_t lastkey = 0;
-        uint32_t k = 0, alive = 0;
-        uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0;      // last scored pattern
-        if (round > 0 && have) {
-            const PromptState& ps = pst_prev[rb.src[p]];
-            k = ps.k; alive = ps.alive;
-            pv0 = ps.pat[0]; pv1 = ps.pat[1]; pv2 = ps.pat[2]; pv3 = ps.pat[3]; pv4 = ps.pat[4]; pvc = ps.pat[5];
-            for (uint32_t q = 0; q < k; ++q) { W.sc[q][lane] = ps.sc[q]; W.pod[q][lane] = ps.pod[q]; W.bt[q][lane] = ps.bt[q]; }
-        }
-        const uint64_t* frow = nullptr;
-        const int nb_max = __reduce_max_sync(0xffffffffu, nb);
-        bool done = !have || nb == 0;                          // walk ended (miss / no live pod); scores are final
-        // slot pair of block 0
-        // (An L2 prefetch running 8 blocks ahead of the walk was tried and made this kernel 2x slower -- DRAM reads
-        //  grew 50 % and issue utilisation fell to 11 %; profiles/r1d_*.  The SM's outstanding-miss capacity, not the
-        //  DRAM latency of a single chain, is what bounds it; the batch is sorted by prefix instead so that lanes of
-        //  a warp ask for the same slots.)
-        uint64_t key = 0, slot = 0;
-        const ReqSlot* base = t.req;                           // table (shard) of the current block's key
-        uint4 A0 = {0, 0, 0, 0}, B0 = {0, 0, 0, 0}, A1 = {0, 0, 0, 0}, B1 = {0, 0, 0, 0};
-        if (!done) {
-            key = rb.keys[ks];
-            const uint64_t hm = home_of(key, mdl);
-            base = t.req_peer[shard_of(hm, t.shard_bits)]; slot = hm & t.req_mask & ~1ull;
-            ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
-        }
-        uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + ks] : 0ull;                         // key of block j+1
-        for (int j = 0; j < nb_max; ++j) {
-            // next block's pair is requested before this block is scored; keys are read one iteration ahead of their use
-            uint64_t nkey = key1, nslot = 0;
-            const ReqSlot* nbase = t.req;
-            uint4 nA0 = {0, 0, 0, 0}, nB0 = {0, 0, 0, 0}, nA1 = {0, 0, 0, 0}, nB1 = {0, 0, 0, 0};
-            const bool nextv = !done && (j + 1 < nb);
-            if (nextv) {
-                const uint64_t hm = home_of(nkey, mdl);
-                nbase = t.req_peer[shard_of(hm, t.shard_bits)]; nslot = hm & t.req_mask & ~1ull;
-                ld_slot_pair(nbase + nslot, peer, nA0, nB0, nA1, nB1);
-            }
-            key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + ks] : 0ull;
-            if (!done && j < nb) {
-                lastkey = key;
-                uint4 A = A0, B = B0;
-                bool hit = slot_matches(A, B, key, mdl);
-                if (!hit && meta_state(B.w) != kStateEmpty) {
-                    A = A1; B = B1;
-                    hit = slot_matches(A, B, key, mdl);
-                    while (!hit && meta_state(B.w) != kStateEmpty) {          // rare: displaced past the home pair
-                        slot = (slot + 2) & t.req_mask;
-                        ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
-                        A = A0; B = B0; hit = slot_matches(A, B, key, mdl);
-                        if (!hit && meta_state(B.w) != kStateEmpty) { A = A1; B = B1; hit = slot_matches(A, B, key, mdl); }
-                    }
-                }
-                if (!hit) { done = true; }
-                else {
-                    SlotWords sw; sw.a = A; sw.b = B;
-                    const uint32_t cnt = meta_count(B.w);
-                    const bool first_block = (round == 0 && j == 0);
-                    const bool same = !first_block && (((pv0 ^ A.z) | (pv1 ^ A.w) | (pv2 ^ B.x) | (pv3 ^ B.y) | (pv4 ^ B.z) | (pvc ^ cnt)) == 0u);
-                    if (same) {
-                        uint32_t am = alive;
-                        while (am) {
-                            const int q = __ffs(am) - 1; am &= am - 1;
-                            const uint32_t bt = W.bt[q][lane];
-                            const double mx = bt == 0xffu ? 0.0 : sm.weight[bt];
-                            W.sc[q][lane] = __dadd_rn(W.sc[q][lane], mx);
-                        }
-                    } else if (first_block) {
-                        // activePods := pods of block 0 (after the filter); score = max weight   (kvblock_scorer.go:118-128)
-                        frow = filter_row(a.filter, p, t.filter_words);
-                        k = 0;
-                        for (uint32_t e = 0; e < cnt; ++e) {
-                            const uint32_t pt = slot_ent(sw, e), pd = pt >> 4;
-                            if (frow && !filter_has(frow, pd)) continue;
-                            const double wt = sm.weight[pt & 15u];
-                            uint32_t q = 0;
-                            for (; q < k; ++q) if (W.pod[q][lane] == pd) break;
-                            if (q == k) { W.pod[k][lane] = (uint16_t)pd; W.sc[k][lane] = 0.0; W.bt[k][lane] = 0xffu; ++k; }
-                            if (wt > W.sc[q][lane]) { W.sc[q][lane] = wt; W.bt[q][lane] = (uint8_t)(pt & 15u); }
-                        }
-                        alive = (1u << k) - 1u;
-                    } else {
-                        // activePods &= pods(block); score[p] += max weight, in block order   (kvblock_scorer.go:130-147)
-                        uint32_t am = alive;
-                        while (am) {
-                            const int q = __ffs(am) - 1; am &= am - 1;
-                            const uint32_t want = W.pod[q][lane];
-                            double mx = 0.0; bool present = false; uint32_t bt = 0xffu;
-                            for (uint32_t e = 0; e < cnt; ++e) {
-                                const uint32_t pt = slot_ent(sw, e);
-                                if ((pt >> 4) == want) { present = true; const double wt = sm.weight[pt & 15u]; if (wt > mx) { mx = wt; bt = pt & 15u; } }
-                            }
-                            if (present) { W.sc[q][lane] = __dadd_rn(W.sc[q][lane], mx); W.bt[q][lane] = (uint8_t)bt; }
-                            else alive &= ~(1u << q);
-                        }
-                    }
-                    pv0 = A.z; pv1 = A.w; pv2 = B.x; pv3 = B.y; pv4 = B.z; pvc = cnt;
-                    if (!alive) done = true;
-                    else {
-                        nwalk = (uint32_t)j + 1u;
-                        if (snapf) {                        // (this kernel snapshots every block: each is its own run)
-                            rb.snap_alive[(size_t)i * kRoundBlocks + j] = (uint16_t)alive;
-                            rb.snap_run[(size_t)i * kRoundBlocks + j] = (uint8_t)j;
-                            double* sd = rb.snap_sc + ((size_t)i * kRoundBlocks + j) * kMaxEnt;
-                            for (uint32_t q = 0; q < k; ++q) sd[q] = W.sc[q][lane];
-                        }
-                    }
-                }
-            }
-            key = nkey; slot = nslot; base = nbase; A0 = nA0; B0 = nB0; A1 = nA1; B1 = nB1;
-        }
-        // ---- continue next round, or write the result ----
-        const bool more = have && !done && has_more;           // all blocks of the round hit, pods still live, blocks left
-        const uint32_t mm = __ballot_sync(0xffffffffu, more);
-        if (mm) {
-            unsigned int base = 0;
-            if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (more) {
-                { const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u)); rb.act[cur ^ 1][ns] = p; rb.lslot[p] = ns; }
-                PromptState& ps = pst_cur[p];
-                rb.hstate[p] = lastkey;                          // chain state for the next round (key of this round's last block)
-                rb.src[p] = p; rb.pos[p] = (round > 0 ? rb.pos[p] : 0u) + (uint32_t)nb;
-                ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
-                ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
-                for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; ps.bt[q] = W.bt[q][lane]; }
-            }
-        }
-        if (have) { rb.fate[li] = more ? kFateMore : kFateDone; rb.nwalk[i] = (uint8_t)nwalk; }
-        if (have && !more) {                                   // final pods and scores, for followers of this class (kernels R, D)
-            PromptState& ps = pst_cur[p];
-            ps.k = (uint8_t)k;
-            for (uint32_t q = 0; q < k; ++q) { ps.sc[q] = W.sc[q][lane]; ps.pod[q] = W.pod[q][lane]; }
-        }
-        __syncwarp();
-        uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
-        while (dm) {                                           // the whole warp writes each finished prompt's row
-            const int l = __ffs(dm) - 1; dm &= dm - 1;
-            const uint32_t pp = __shfl_sync(0xffffffffu, p, l);
-            const uint32_t pk = __shfl_sync(0xffffffffu, k, l);
-            const uint32_t pmeta = __shfl_sync(0xffffffffu, meta, l);
-            if (a.dense) {
-                double* row = a.dense + (long long)pp * t.max_pods;
-                const uint32_t P = t.max_pods;
-                if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
-                } else {
-                    for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
-                }
-                __syncwarp();
-                if ((uint32_t)lane < pk) { const uint32_t pd = W.pod[lane][l]; if (pd < P) row[pd] = W.sc[lane][l]; }
-            }
-            if (a.sp_cnt) {
-                if ((uint32_t)lane < pk) { a.sp_pods[(long long)pp * kMaxEnt + lane] = W.pod[lane][l]; a.sp_scores[(long long)pp * kMaxEnt + lane] = W.sc[lane][l]; }
-                if (lane == 0) a.sp_cnt[pp] = (uint8_t)pk;
-            }
-            if (a.has_keys && lane == 0) a.has_keys[pp] = (round > 0) || (pmeta & 63u) > 0;
-        }
-        __syncwarp();
-    }
-}
-
-// ---- kernel P, warp per representative ------------------------------------------------------------------------
-// With prefix classes the representatives of a round are few (one per distinct prefix), so the lane-per-prompt walk
-// above -- 32 dependent iterations of a few hundred divergent instructions -- leaves the machine idle: its time is a
-// latency chain that does not shrink with the list.  Here a warp takes one representative: the 32 lanes probe the
+// ---- kernel P: warp per representative ------------------------------------------------------------------------
+// With prefix classes the representatives of a round are few (one per distinct prefix), so a lane-per-prompt walk
+// (kernels_rounds_plain.cuh: 32 dependent iterations of divergent code per warp) would leave the machine idle: its time
+// is a latency chain that does not shrink with the list.  Here a warp takes one representative: the 32 lanes probe the
 // round's 32 keys at once (one DRAM latency for the whole chunk), a ballot finds the first miss, and the blocks before
 // it are scored in order with lane q owning pod q of the first block (<= 10 pods), the block's entries broadcast by
 // shuffle.  Same arithmetic in the same order as everywhere else: max weight per pod per block, added in block order.
@@ -902,14 +696,14 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
 // Lane per follower.  Representative continues: so does the follower, with the representative's chain state, and its
 // walk state stays where the representative left it (src).  Representative finished: same pods, same scores -- the warp
 // writes the follower's result from the representative's final state.
-__device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int reps_too,
+__device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round,
                                               const unsigned int bid, const unsigned int nbl) {
     const int lane = threadIdx.x & 31;
     {   // kernel P is done with need_snap: clear it for the next round
         uint32_t* f4 = reinterpret_cast<uint32_t*>(rb.need_snap);
         for (size_t x = bid * (size_t)blockDim.x + threadIdx.x; x < rb.part_size / 4; x += (size_t)nbl * blockDim.x) f4[x] = 0u;
     }
-    if (reps_too) {                                            // representatives that continue (walk_round_kernel leaves the list to us)
+    {                                                          // representatives that continue (walk_round_kernel leaves the list to us)
         const unsigned int n_a = rb.n_hl[0];
         const unsigned int tw = nbl * (blockDim.x / 32);
         for (unsigned int w = bid * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_a; w += tw) {
@@ -1122,13 +916,13 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
 // live list, which both append to).
 template <int BS>
 __global__ void __launch_bounds__(256)
-finish_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int reps_too, const int detach, const int trace) {
+finish_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int detach, const int trace) {
     __shared__ DetachSmem sm;
-    if (!detach) { resolve_round(t, a, rb, cur, round, reps_too, blockIdx.x, gridDim.x); return; }
+    if (!detach) { resolve_round(t, a, rb, cur, round, blockIdx.x, gridDim.x); return; }
     // odd CTAs take the followers, even CTAs the partial followers: the two latency chains run side by side
     const unsigned int half = gridDim.x / 2;
-    if (gridDim.x < 2) { resolve_round(t, a, rb, cur, round, reps_too, 0, 1); detach_round<BS>(t, a, rb, cur, round, trace, sm, 0, 1); }
-    else if (blockIdx.x & 1) { if (blockIdx.x / 2 < half) resolve_round(t, a, rb, cur, round, reps_too, blockIdx.x / 2, half); }
+    if (gridDim.x < 2) { resolve_round(t, a, rb, cur, round, 0, 1); detach_round<BS>(t, a, rb, cur, round, trace, sm, 0, 1); }
+    else if (blockIdx.x & 1) { if (blockIdx.x / 2 < half) resolve_round(t, a, rb, cur, round, blockIdx.x / 2, half); }
     else detach_round<BS>(t, a, rb, cur, round, trace, sm, blockIdx.x / 2, (gridDim.x + 1) / 2);
 }
 
@@ -1160,7 +954,6 @@ __global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsig
 
 inline int rounds_init() {
     if (cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(probe_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(group_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)) != cudaSuccess) return -1;
     return 0;
 }

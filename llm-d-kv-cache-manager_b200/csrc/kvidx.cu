@@ -101,11 +101,8 @@ struct kvidx {
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
     int64_t classes_min = 393216;  // ... and at least this large, the prefix-class round pipeline
     DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate, r_anch, r_snap, r_rec;
-    int rounds_stagger = -1;       // (measured: no gain) part q+1 starts after part q's round-0 kernel number this (0 group, 1 lists, 2 hash; -1: together)
-    cudaEvent_t ev_stag[kMaxParts] = {};
     int rounds_trace = 0;
     int rounds_grid[5] = {2, 4, 2, 4, 4};   // CTAs per SM a part's group / lists / hash / walk / finish kernel may occupy (multi-part runs)
-    int rounds_walk = 1;           // kernel P: 1 warp per representative, 0 lane per representative
     int rounds_parts = 8;          // parts (streams) a large batch is split into
     int rounds_dedup = 2;          // round pipeline: 0 every prompt on its own, 1 prefix classes, 2 + partial followers
     int sort_prefix = 1;           // sort the batch by first-block fingerprint before the rounds
@@ -299,7 +296,6 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         CK(cudaEventRecord(x->ev_fork, st));
         for (int q = 1; q < np; ++q) CK(cudaStreamWaitEvent(strm[q], x->ev_fork, 0));
     }
-    const int per_sm = np == 1 ? 4 : 2;
     const auto t_enq = std::chrono::steady_clock::now();
     for (int64_t r = 0; r < rounds; ++r) {
         const int cur = (int)(r & 1);
@@ -307,29 +303,15 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
             const int64_t m = psz[q];
             if (m <= 0) continue;
             const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads - 1) / kGroupThreads, (int64_t)x->sm_count * (np == 1 ? 3 : x->rounds_grid[0]));
-            // Parts of equal size would march through the same phase at the same time (all streaming tokens, then all waiting on
-            // a serial hash chain): each part starts when its predecessor has finished a kernel of round 0, so that their
-            // bandwidth-bound and latency-bound kernels interleave.
-            if (r == 0 && q > 0 && x->rounds_stagger >= 0) CK(cudaStreamWaitEvent(strm[q], x->ev_stag[q - 1], 0));
             group_round_kernel<16><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
-            if (r == 0 && x->rounds_stagger == 0) CK(cudaEventRecord(x->ev_stag[q], strm[q]));
             const unsigned lgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : x->rounds_grid[1]));
             group_lists_kernel<16><<<lgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2);
-            if (r == 0 && x->rounds_stagger == 1) CK(cudaEventRecord(x->ev_stag[q], strm[q]));
             const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * (np == 1 ? 4 : x->rounds_grid[2]));
             hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
-            if (r == 0 && x->rounds_stagger == 2) CK(cudaEventRecord(x->ev_stag[q], strm[q]));
-            const unsigned pgrid = (unsigned)std::min<int64_t>((m + kProbeThreads - 1) / kProbeThreads, (int64_t)x->sm_count * per_sm);
-            if (x->rounds_walk == 1) {
-                const unsigned wgrid = (unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)x->sm_count * (np == 1 ? 8 : x->rounds_grid[3]));
-                walk_round_kernel<<<wgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
-            } else {
-                probe_round_kernel<<<pgrid, kProbeThreads, sizeof(WalkSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
-            }
-            {
-                const unsigned rgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : x->rounds_grid[4]));
-                finish_round_kernel<16><<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_walk == 1, x->rounds_dedup >= 2, x->rounds_trace);
-            }
+            const unsigned wgrid = (unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)x->sm_count * (np == 1 ? 8 : x->rounds_grid[3]));
+            walk_round_kernel<<<wgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
+            const unsigned rgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : x->rounds_grid[4]));
+            finish_round_kernel<16><<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2, x->rounds_trace);
             x->launches += 5;
             if (x->rounds_trace == 1) {      // debugging aid: list sizes of this round (synchronises)
                 unsigned int c[8];
@@ -658,7 +640,6 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
         CK(cudaEventCreateWithFlags(&x->ev_join[q], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
-    for (int q = 0; q < kMaxParts; ++q) CK(cudaEventCreateWithFlags(&x->ev_stag[q], cudaEventDisableTiming));
     x->stream = x->own_stream;
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
@@ -701,9 +682,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_CLASSES_MIN")) x->classes_min = atoll(k);
     if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
-    if (const char* k = getenv("KVIDX_ROUNDS_WALK")) x->rounds_walk = !strcmp(k, "lane") ? 0 : 1;
     if (const char* k = getenv("KVIDX_ROUNDS_GRID")) sscanf(k, "%d,%d,%d,%d,%d", &x->rounds_grid[0], &x->rounds_grid[1], &x->rounds_grid[2], &x->rounds_grid[3], &x->rounds_grid[4]);
-    if (const char* k = getenv("KVIDX_ROUNDS_STAGGER")) x->rounds_stagger = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_TRACE")) x->rounds_trace = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);
@@ -741,7 +720,6 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_join[q]) cudaEventDestroy(x->ev_join[q]);
     }
     if (x->ev_fork) cudaEventDestroy(x->ev_fork);
-    for (int q = 0; q < kMaxParts; ++q) if (x->ev_stag[q]) cudaEventDestroy(x->ev_stag[q]);
     delete x;
 }
 

@@ -269,7 +269,7 @@ def _select_path(monkeypatch, path):
     """v1: thread-per-prompt kernel; fused: persistent lane-worker kernel; rounds*: hash / walk rounds, every prompt on
     its own (one stream / two halves on two streams / without the prefix sort); classes*: the round pipeline that hashes
     and walks one representative per distinct prefix (one part / 2 / 8 parts / unsorted / sharing switched off / whole
-    chunks only, no partial followers / lane-per-representative walk kernel)."""
+    chunks only, no partial followers)."""
     if path == "v1":
         monkeypatch.setenv("KVIDX_SCORE_KERNEL", "v1")
         return
@@ -288,12 +288,10 @@ def _select_path(monkeypatch, path):
         monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "0")
     elif var == "whole":
         monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "1")
-    elif var == "lane":
-        monkeypatch.setenv("KVIDX_ROUNDS_WALK", "lane")
 
 
 ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "classes", "classes2", "classes8", "classes-nosort", "classes-nodedup", "classes-whole",
-               "classes4-lane"]
+               "classes4-whole"]
 PATHS = ["v1", "fused"] + ROUND_PATHS
 
 
@@ -421,7 +419,7 @@ def test_rounds_prefix_sharing_heavy_overlap(kernel, monkeypatch):
     assert np.array_equal(s_t, s_o), np.argwhere(s_t != s_o)[:5]
 
 
-@pytest.mark.parametrize("kernel", ["rounds2", "classes", "classes8", "classes-whole", "classes4-lane"])
+@pytest.mark.parametrize("kernel", ["rounds2", "classes", "classes8", "classes-whole", "classes4-nosort"])
 def test_prefix_tree_workload(kernel, monkeypatch):
     """Prompts drawn from a random prefix TREE (conversations forking off shared history at arbitrary token positions,
     several levels deep), every branch cached on its own pods up to a random depth.  Prompts leave popular prefixes in
