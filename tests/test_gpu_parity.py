@@ -462,6 +462,48 @@ def test_prefix_tree_workload(kernel, monkeypatch):
         assert got == {int(q): float(s_o[i, q]) for q in np.nonzero(s_o[i] >= 0)[0]}
 
 
+@pytest.mark.parametrize("kernel", ["classes", "classes8", "rounds2"])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_tiny_alphabet_fuzz(kernel, seed, monkeypatch):
+    """Prompts over a two-letter alphabet: every pair of prompts shares a prefix of some random length, chunks coincide in
+    all sorts of partial ways, lengths are ragged, duplicates abound -- and about half of all short chains are cached.
+    Plus the degenerate batch sizes (1, 5, 33 prompts).  Bit-exact vs the oracle."""
+    _select_path(monkeypatch, kernel)
+    rng = np.random.default_rng(900 + seed)
+    BS, P = 16, 24
+    ix, co = _index_pair(capacity=1 << 15, max_pods=P)
+    base = [rng.integers(0, 2, size=int(rng.integers(BS, 1400)), dtype=np.uint32) * 7 for _ in range(40)]
+    # long runs of equal blocks make distinct prompts agree for a while and then part ways
+    for b in base:
+        b[: BS * int(rng.integers(0, 30))] = 0
+    for b in base[:25]:
+        keys = ix.hash_keys(b, np.array([0, len(b)], np.int64))[0]
+        if len(keys) == 0:
+            continue
+        nb = int(rng.integers(1, len(keys) + 1))
+        pt = [(int(rng.integers(0, P)) << 4) | int(rng.integers(0, 2)) for _ in range(int(rng.integers(1, 4)))]
+        eng = (keys[:nb] ^ np.uint64(0x77)).astype(np.uint64)
+        assert ix.add(0, eng, keys[:nb], pt) == 0
+        co.add(0, eng, keys[:nb], pt)
+    prompts = []
+    for i in range(5000):
+        b = base[int(rng.integers(0, len(base)))]
+        pr = b[: int(rng.integers(0, len(b) + 1))].copy()
+        if i % 4 == 0 and len(pr):
+            pr[int(rng.integers(0, len(pr))):] = 7                      # a different tail from some position on
+        prompts.append(pr)
+    for n in (len(prompts), 1, 5, 33):
+        tok, off = csr(prompts[:n])
+        s_t, h_t = ix.score_batch(tok, off)
+        s_o, h_o, _, _ = co.score_batch(tok, off, n_threads=4)
+        assert np.array_equal(h_t, h_o) and np.array_equal(s_t, s_o), (n, np.argwhere(s_t != s_o)[:5])
+    same = [base[0]] * 3000                                             # one prompt, three thousand times
+    tok, off = csr(same)
+    s_t, _ = ix.score_batch(tok, off)
+    s_o, _, _, _ = co.score_batch(tok, off, n_threads=4)
+    assert np.array_equal(s_t, s_o) and (s_t == s_t[0]).all()
+
+
 def test_config5_scores_while_the_write_path_runs():
     """BASELINE config #5 in miniature: one thread keeps storing and removing documents through apply_events while another
     scores prompts of documents the writer never touches.  Calls on one handle serialise, so every Score() sees the index
