@@ -101,6 +101,7 @@ struct kvidx {
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
     int64_t classes_min = 393216;  // ... and at least this large, the prefix-class round pipeline
     DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate, r_anch, r_snap, r_rec;
+    int64_t host_chunk_tokens = 32ll << 20;   // tokens per H2D chunk of the host-buffer pipeline
     int rounds_trace = 0;
     int rounds_grid[5] = {2, 4, 2, 4, 4};   // CTAs per SM a part's group / lists / hash / walk / finish kernel may occupy (multi-part runs)
     int rounds_parts = 8;          // parts (streams) a large batch is split into
@@ -448,7 +449,7 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
     const size_t out_row = sparse ? (size_t)kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 2 : (size_t)P * sizeof(double) + 1;
     // chunk = up to 32 Mi tokens (128 MiB): the H2D copy of a chunk (2.3 ms at 55 GB/s) must outlast its kernel
     // (~1 ms for 8192 x 4K-token prompts) for the pipeline to be PCIe bound; 8 Mi-token chunks were kernel bound.
-    const int64_t kMaxTokChunk = 32ll << 20;
+    const int64_t kMaxTokChunk = x->host_chunk_tokens;
     const int64_t kMaxRowsChunk = std::max<int64_t>(1, (128ll << 20) / (int64_t)out_row);
     const bool tok_pinned = tok && is_device_accessible_host(tok);
     const bool out_pinned = !sparse && dense && is_device_accessible_host(dense) && (!has_keys || is_device_accessible_host(has_keys));
@@ -683,6 +684,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_GRID")) sscanf(k, "%d,%d,%d,%d,%d", &x->rounds_grid[0], &x->rounds_grid[1], &x->rounds_grid[2], &x->rounds_grid[3], &x->rounds_grid[4]);
+    if (const char* k = getenv("KVIDX_HOST_CHUNK_TOKENS")) x->host_chunk_tokens = std::max<int64_t>(1 << 16, atoll(k));
     if (const char* k = getenv("KVIDX_ROUNDS_TRACE")) x->rounds_trace = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);
