@@ -410,7 +410,7 @@ int launch_score(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t 
         score_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
                                                                   o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, sb, stride);
         x->launches += 1;
-    } else if (x->tv.block_size == 16 && n < (1ll << 32) && (x->score_path >= 2 || (x->score_path == 0 && n >= x->rounds_min))) {
+    } else if (x->tv.block_size == 16 && n < (1ll << 31) && (x->score_path >= 2 || (x->score_path == 0 && n >= x->rounds_min))) {
         // path 2: plain rounds, 3: prefix classes; automatic: by batch size (the class pipeline has a fixed cost per round)
         const bool classes = x->score_path == 3 || (x->score_path == 0 && n >= x->classes_min);
         return classes ? launch_score_rounds(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks)
