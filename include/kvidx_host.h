@@ -12,6 +12,7 @@
  *   kvhost_pool_add_task     <-> kvevents.Pool.AddTask                pkg/kvcache/kvevents/pool.go:132-144
  *   kvhost_pool_process      <-> worker loop: processEvent + digestEvents       pkg/kvcache/kvevents/pool.go:149-338
  *   kvhost_decode_event_batch<-> processEvent's msgpack decoding      pkg/kvcache/kvevents/pool.go:177-244, events.go:38-96
+ *   kvhost_get_metrics / _text <-> InstrumentedIndex + collectors      pkg/kvcache/kvblock/instrumented_index.go:30-92, metrics/collector.go:28-59
  */
 #ifndef KVIDX_HOST_H
 #define KVIDX_HOST_H
@@ -30,6 +31,7 @@ typedef struct kvhost_config {
     const char* tier_names[KVIDX_MAX_TIERS];
     double tier_weights[KVIDX_MAX_TIERS];
     int32_t no_device;               /* 1: host-only instance (interners, queues, decoder) without a kvidx handle       */
+    int32_t enable_metrics;          /* IndexConfig.EnableMetrics (index.go:41-43): wrap the index in the instrumented one */
 } kvhost_config_t;
 
 void kvhost_config_default(kvhost_config_t* cfg);       /* block 16, seed "", gpu 1.0 / cpu 0.8, concurrency 4 */
@@ -68,6 +70,25 @@ int64_t kvhost_pool_process(kvhost_t* h, int64_t* n_dropped_out);
 int64_t kvhost_decode_event_batch(kvhost_t* h, const char* pod, const char* model, const void* payload, size_t len,
                                   kvidx_event_t* ev_out, size_t ev_cap, uint64_t* hash_out, size_t hash_cap, size_t* n_hash_out,
                                   uint32_t* tok_out, size_t tok_cap, size_t* n_tok_out);
+
+/* kvcache_index_* metrics (metrics/collector.go:28-59) with the instrumented index's semantics (instrumented_index.go:35-92):
+ * Add counts len(requestKeys) admissions and Evict len(entries) evictions whatever the call returned; every Lookup counts
+ * one request and one latency observation; a successful Lookup adds max over pods of that pod's entries in the result to
+ * both max_pod_hit_count and lookup_hits.  The event pool goes through the same Add / Evict (one Evict per removed hash,
+ * pool.go:317-330).  With enable_metrics, kvhost_get_pod_scores issues the reference's full-depth Lookup
+ * (kvidx_hash_keys + kvidx_lookup on the device) next to the fused score call, because the hit count needs every key of
+ * the prompt, not only the consecutive prefix the scorer walks.  All zero when enable_metrics is 0. */
+#define KVHOST_LATENCY_BUCKETS 11          /* prometheus.DefBuckets: .005 .01 .025 .05 .1 .25 .5 1 2.5 5 10 (+Inf = count) */
+typedef struct kvhost_metrics {
+    uint64_t admissions_total, evictions_total, lookup_requests_total, max_pod_hit_count_total, lookup_hits_total;
+    uint64_t lookup_latency_bucket[KVHOST_LATENCY_BUCKETS];      /* cumulative, le = bucket bound */
+    uint64_t lookup_latency_count;
+    double lookup_latency_sum;                                   /* seconds */
+} kvhost_metrics_t;
+int kvhost_get_metrics(kvhost_t* h, kvhost_metrics_t* out);
+/* Prometheus text exposition of the above (same metric names and help strings as the reference).  Returns the number of
+ * bytes needed (excluding the NUL); writes at most cap - 1 bytes + NUL. */
+int64_t kvhost_metrics_text(kvhost_t* h, char* buf, size_t cap);
 
 /* interning introspection (ids are append-only and never reused) */
 int kvhost_pod_id(kvhost_t* h, const char* pod);

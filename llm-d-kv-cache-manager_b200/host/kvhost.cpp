@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cstring>
+#include <chrono>
 #include <deque>
 #include <mutex>
 #include <string>
@@ -127,6 +128,7 @@ struct kvhost {
     std::mutex mu;
     std::vector<std::deque<Msg>> queues;
     uint32_t filter_words = 4;
+    kvhost_metrics_t met{};              // guarded by mu
 };
 
 namespace {
@@ -240,6 +242,8 @@ void decode_batch(kvhost* h, uint32_t pod, uint32_t model, const uint8_t* p, siz
 
 }  // namespace
 
+static const double kLatencyBuckets[KVHOST_LATENCY_BUCKETS] = {0.005, 0.01, 0.025, 0.05, 0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0};   // prometheus.DefBuckets
+
 extern "C" {
 
 const char* kvhost_last_error(void) { return g_herr.c_str(); }
@@ -282,11 +286,60 @@ int kvhost_create(const kvhost_config_t* cfg_in, const char* hash_seed, kvhost_t
 void kvhost_destroy(kvhost_t* h) { if (!h) return; if (h->ix) kvidx_destroy(h->ix); delete h; }
 kvidx_t* kvhost_index(kvhost_t* h) { return h ? h->ix : nullptr; }
 
+int kvhost_get_metrics(kvhost_t* h, kvhost_metrics_t* out) {
+    if (!h || !out) return hfail(KVIDX_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(h->mu);
+    *out = h->met;
+    return 0;
+}
+
+int64_t kvhost_metrics_text(kvhost_t* h, char* buf, size_t cap) {
+    kvhost_metrics_t m;
+    if (kvhost_get_metrics(h, &m)) return KVIDX_EINVAL;
+    std::string s;
+    auto counter = [&](const char* name, const char* help, uint64_t v) {
+        s += "# HELP kvcache_index_"; s += name; s += " "; s += help; s += "\n# TYPE kvcache_index_"; s += name; s += " counter\nkvcache_index_";
+        s += name; s += " " + std::to_string(v) + "\n";
+    };
+    counter("admissions_total", "Total number of KV-block admissions", m.admissions_total);
+    counter("evictions_total", "Total number of KV-block evictions", m.evictions_total);
+    counter("lookup_requests_total", "Total number of lookup calls", m.lookup_requests_total);
+    counter("max_pod_hit_count_total", "Maximum cache hits on a single pod on Lookup()", m.max_pod_hit_count_total);
+    counter("lookup_hits_total", "Number of keys found in the cache on Lookup()", m.lookup_hits_total);
+    s += "# HELP kvcache_index_lookup_latency_seconds Latency of Lookup calls in seconds\n# TYPE kvcache_index_lookup_latency_seconds histogram\n";
+    char tmp[96];
+    for (int b = 0; b < KVHOST_LATENCY_BUCKETS; ++b) {
+        snprintf(tmp, sizeof tmp, "kvcache_index_lookup_latency_seconds_bucket{le=\"%g\"} %llu\n", kLatencyBuckets[b], (unsigned long long)m.lookup_latency_bucket[b]);
+        s += tmp;
+    }
+    snprintf(tmp, sizeof tmp, "kvcache_index_lookup_latency_seconds_bucket{le=\"+Inf\"} %llu\n", (unsigned long long)m.lookup_latency_count); s += tmp;
+    snprintf(tmp, sizeof tmp, "kvcache_index_lookup_latency_seconds_sum %.9g\n", m.lookup_latency_sum); s += tmp;
+    snprintf(tmp, sizeof tmp, "kvcache_index_lookup_latency_seconds_count %llu\n", (unsigned long long)m.lookup_latency_count); s += tmp;
+    if (buf && cap) { const size_t n = std::min(cap - 1, s.size()); memcpy(buf, s.data(), n); buf[n] = 0; }
+    return (int64_t)s.size();
+}
+
 int kvhost_pod_id(kvhost_t* h, const char* s) { std::lock_guard<std::mutex> g(h->mu); return h->pods.id(s, KVIDX_MAX_PODS); }
 int kvhost_tier_id(kvhost_t* h, const char* s) { std::lock_guard<std::mutex> g(h->mu); return h->tiers.id(lower(s), KVIDX_MAX_TIERS); }
 int kvhost_model_id(kvhost_t* h, const char* s) { std::lock_guard<std::mutex> g(h->mu); return h->models.id(s, 65536); }
 
 static int need_dev(kvhost* h) { return h && h->ix ? 0 : hfail(KVIDX_ECUDA, "host-only instance: no device index (there is no CPU fallback)"); }
+
+// One Lookup as the instrumented index sees it (instrumented_index.go:47-69): request + latency always, hits on success.
+static void observe_lookup(kvhost* h, double seconds, bool ok, const kvidx_podtier_t* pt, const uint8_t* cnt, size_t n) {
+    if (!h->cfg.enable_metrics) return;
+    uint64_t mx = 0;
+    if (ok) {                                           // recordHitMetrics: entries per pod over the whole result
+        std::vector<uint32_t> per(KVIDX_MAX_PODS, 0);
+        for (size_t i = 0; i < n; ++i)
+            for (int j = 0; j < cnt[i]; ++j) { const uint32_t c = ++per[KVIDX_PT_POD(pt[i * KVIDX_MAX_PODS_PER_KEY + j])]; if (c > mx) mx = c; }
+    }
+    std::lock_guard<std::mutex> g(h->mu);
+    h->met.lookup_requests_total += 1;
+    h->met.lookup_latency_count += 1; h->met.lookup_latency_sum += seconds;
+    for (int b = 0; b < KVHOST_LATENCY_BUCKETS; ++b) if (seconds <= kLatencyBuckets[b]) h->met.lookup_latency_bucket[b] += 1;
+    h->met.max_pod_hit_count_total += mx; h->met.lookup_hits_total += mx;
+}
 
 static bool build_filter(kvhost* h, const char* const* pods, size_t n_pods, std::vector<uint64_t>& mask) {
     // sets.New(podIdentifiers...): a name never seen by the index cannot match any entry, but still makes the set non-empty
@@ -308,13 +361,26 @@ int kvhost_get_pod_scores(kvhost_t* h, const uint32_t* tokens, size_t n_tokens, 
     if (mid < 0) return hfail(KVIDX_ERANGE, "too many models");
     if (filtered) {                                 // a filter whose pods all lie outside the mask width selects nothing
         bool any = false; for (uint64_t w : mask) any |= w != 0;
-        if (!any) return n_tokens >= (h->cfg.index.block_size ? h->cfg.index.block_size : 16) ? 0 : -1000;
+        if (!any) {
+            const bool has_keys = n_tokens >= (h->cfg.index.block_size ? h->cfg.index.block_size : 16);
+            if (has_keys) observe_lookup(h, 0.0, true, nullptr, nullptr, 0);      // the Lookup still happens; it just finds no listed pod
+            return has_keys ? 0 : -1000;
+        }
     }
     const int64_t off[2] = {0, (int64_t)n_tokens};
     uint16_t ids[KVIDX_MAX_PODS_PER_KEY]; double sc[KVIDX_MAX_PODS_PER_KEY]; uint8_t cnt = 0, has = 0;
     const int rc = kvidx_score_batch_sparse(h->ix, tokens, off, 1, nullptr, (uint32_t)mid, filtered ? mask.data() : nullptr, ids, sc, &cnt, &has);
     if (rc) { g_herr = kvidx_last_error(h->ix); return rc; }
     if (!has) return -1000;                         // (nil, nil): no full block (indexer.go:142-146)
+    if (h->cfg.enable_metrics) {                    // the instrumented Lookup of indexer.go:150: every key of the prompt
+        const size_t nk = n_tokens / (h->cfg.index.block_size ? h->cfg.index.block_size : 16);
+        std::vector<uint64_t> keys(nk); int64_t koff[2] = {0, 0};
+        std::vector<kvidx_podtier_t> pt(nk * KVIDX_MAX_PODS_PER_KEY); std::vector<uint8_t> kc(nk);
+        int r2 = kvidx_hash_keys(h->ix, tokens, off, 1, nullptr, nullptr, keys.data(), koff);
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!r2) r2 = kvidx_lookup(h->ix, (uint32_t)mid, keys.data(), (int64_t)nk, filtered ? mask.data() : nullptr, pt.data(), kc.data());
+        observe_lookup(h, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(), r2 == 0, pt.data(), kc.data(), nk);
+    }
     std::lock_guard<std::mutex> g(h->mu);
     for (int i = 0; i < cnt; ++i) { pod_out[i] = h->pods.names[ids[i]].c_str(); score_out[i] = sc[i]; }
     return cnt;
@@ -333,6 +399,7 @@ static int entries_of(kvhost* h, const char* const* pods, const char* const* tie
 int kvhost_index_add(kvhost_t* h, const char* model, const uint64_t* engine, size_t n_engine, const uint64_t* request, size_t n_request,
                      const char* const* pods, const char* const* tiers, size_t n_entries) {
     if (int rc = need_dev(h)) return rc;
+    if (h->cfg.enable_metrics) { std::lock_guard<std::mutex> g(h->mu); h->met.admissions_total += n_request; }   // whatever Add returns
     if (n_engine == 0 || n_request == 0 || n_entries == 0) return hfail(KVIDX_EINVAL, "no keys or entries provided for adding to index");
     if (n_engine != n_request) return hfail(KVIDX_EINVAL, "mismatch between engine keys and request keys length");
     std::vector<kvidx_podtier_t> pt; int mid;
@@ -344,6 +411,7 @@ int kvhost_index_add(kvhost_t* h, const char* model, const uint64_t* engine, siz
 
 int kvhost_index_evict(kvhost_t* h, const char* model, uint64_t engine, const char* const* pods, const char* const* tiers, size_t n_entries) {
     if (int rc = need_dev(h)) return rc;
+    if (h->cfg.enable_metrics) { std::lock_guard<std::mutex> g(h->mu); h->met.evictions_total += n_entries; }
     if (n_entries == 0) return hfail(KVIDX_EINVAL, "no entries provided for eviction from index");
     std::vector<kvidx_podtier_t> pt; int mid;
     { std::lock_guard<std::mutex> g(h->mu); if (int rc = entries_of(h, pods, tiers, n_entries, pt)) return rc; mid = h->models.id(model, 65536); }
@@ -363,12 +431,15 @@ int kvhost_index_get_request_key(kvhost_t* h, const char* model, uint64_t engine
 int kvhost_index_lookup(kvhost_t* h, const char* model, const uint64_t* keys, size_t n, const char* const* pods, size_t n_pods,
                         const char** pod_out, const char** tier_out, uint8_t* cnt_out) {
     if (int rc = need_dev(h)) return rc;
-    if (n == 0) return hfail(KVIDX_EINVAL, "no requestKeys provided for lookup");
+    const auto t0 = std::chrono::steady_clock::now();
+    auto secs = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    if (n == 0) { observe_lookup(h, secs(), false, nullptr, nullptr, 0); return hfail(KVIDX_EINVAL, "no requestKeys provided for lookup"); }
     std::vector<uint64_t> mask; bool filtered; int mid;
     { std::lock_guard<std::mutex> g(h->mu); filtered = build_filter(h, pods, n_pods, mask); mid = h->models.id(model, 65536); }
     std::vector<kvidx_podtier_t> pt(n * KVIDX_MAX_PODS_PER_KEY);
-    if (filtered) { bool any = false; for (uint64_t w : mask) any |= w != 0; if (!any) { memset(cnt_out, 0, n); return 0; } }
+    if (filtered) { bool any = false; for (uint64_t w : mask) any |= w != 0; if (!any) { memset(cnt_out, 0, n); observe_lookup(h, secs(), true, pt.data(), cnt_out, n); return 0; } }
     const int rc = kvidx_lookup(h->ix, (uint32_t)mid, keys, (int64_t)n, filtered ? mask.data() : nullptr, pt.data(), cnt_out);
+    observe_lookup(h, secs(), rc == 0, pt.data(), cnt_out, n);
     if (rc) { g_herr = kvidx_last_error(h->ix); return rc; }
     std::lock_guard<std::mutex> g(h->mu);
     for (size_t i = 0; i < n; ++i)
@@ -402,6 +473,16 @@ int64_t kvhost_pool_process(kvhost_t* h, int64_t* n_dropped_out) {
         }
     }
     if (n_dropped_out) *n_dropped_out = 0;
+    if (h->cfg.enable_metrics) {                       // digestEvents calls the instrumented Add / Evict (pool.go:299-330)
+        const uint32_t bs = h->cfg.index.block_size ? h->cfg.index.block_size : 16;
+        uint64_t adm = 0, evi = 0;
+        for (const auto& e : evs) {
+            if (e.op == KVIDX_EV_BLOCK_STORED) { if (e.n_hashes > 0) adm += e.n_tokens / bs; }      // Add(len(requestKeys)) only if there are engine keys
+            else if (e.op == KVIDX_EV_BLOCK_REMOVED) evi += e.n_hashes;                             // one Evict with one entry per hash
+        }
+        std::lock_guard<std::mutex> g(h->mu);
+        h->met.admissions_total += adm; h->met.evictions_total += evi;
+    }
     if (evs.empty()) return 0;
     const int rc = kvidx_apply_events(h->ix, evs.data(), (int64_t)evs.size(), hashes.data(), (int64_t)hashes.size(), toks.data(), (int64_t)toks.size(), n_dropped_out);
     if (rc) { g_herr = kvidx_last_error(h->ix); return rc; }

@@ -14,7 +14,16 @@ NO_KEYS = -1000
 
 class HostConfig(C.Structure):
     _fields_ = [("index", Config), ("concurrency", C.c_uint32), ("n_tiers", C.c_uint32), ("tier_names", C.c_char_p * MAX_TIERS),
-                ("tier_weights", C.c_double * MAX_TIERS), ("no_device", C.c_int32)]
+                ("tier_weights", C.c_double * MAX_TIERS), ("no_device", C.c_int32), ("enable_metrics", C.c_int32)]
+
+
+LATENCY_BUCKETS = 11
+
+
+class HostMetrics(C.Structure):
+    _fields_ = [("admissions_total", C.c_uint64), ("evictions_total", C.c_uint64), ("lookup_requests_total", C.c_uint64),
+                ("max_pod_hit_count_total", C.c_uint64), ("lookup_hits_total", C.c_uint64), ("lookup_latency_bucket", C.c_uint64 * LATENCY_BUCKETS),
+                ("lookup_latency_count", C.c_uint64), ("lookup_latency_sum", C.c_double)]
 
 
 _cpp = C.POINTER(C.c_char_p)
@@ -23,6 +32,8 @@ SYMBOLS = {
     "kvhost_config_default": (None, [C.POINTER(HostConfig)]),
     "kvhost_create": (C.c_int, [C.POINTER(HostConfig), C.c_char_p, C.POINTER(C.c_void_p)]),
     "kvhost_destroy": (None, [C.c_void_p]),
+    "kvhost_get_metrics": (C.c_int, [C.c_void_p, C.POINTER(HostMetrics)]),
+    "kvhost_metrics_text": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "kvhost_last_error": (C.c_char_p, []),
     "kvhost_index": (C.c_void_p, [C.c_void_p]),
     "kvhost_get_pod_scores": (C.c_int, [C.c_void_p, _u32p, C.c_size_t, C.c_char_p, _cpp, C.c_size_t, _cpp, _f64p]),
@@ -64,13 +75,14 @@ class HostIndexer:
     """kvcache.Indexer + kvblock.Index + kvevents.Pool with strings (pods, tiers, models are names)."""
 
     def __init__(self, block_size=16, hash_seed="", capacity=1 << 20, pods_per_key=10, tiers=(("gpu", 1.0), ("cpu", 0.8)), max_pods=256,
-                 concurrency=4, device=0, no_device=False, lru_exact=0):
+                 concurrency=4, device=0, no_device=False, lru_exact=0, enable_metrics=False):
         self.L = _lib()
         cfg = HostConfig()
         self.L.kvhost_config_default(C.byref(cfg))
         cfg.index.block_size, cfg.index.capacity, cfg.index.pods_per_key = block_size, capacity, pods_per_key
         cfg.index.max_pods, cfg.index.device, cfg.index.lru_exact = max_pods, device, lru_exact
         cfg.concurrency, cfg.n_tiers, cfg.no_device = concurrency, len(tiers), 1 if no_device else 0
+        cfg.enable_metrics = 1 if enable_metrics else 0
         self._tier_names = [t[0].encode() for t in tiers]
         for i, (n, w) in enumerate(tiers):
             cfg.tier_names[i] = self._tier_names[i]
@@ -127,6 +139,22 @@ class HostIndexer:
         if rc:
             return rc, {}
         return 0, {int(k[i]): [(po[i * 10 + j].decode(), to[i * 10 + j].decode()) for j in range(cnt[i])] for i in range(n) if cnt[i]}
+
+    def metrics(self):
+        """kvcache_index_* counters as a dict (all zero unless enable_metrics)."""
+        m = HostMetrics()
+        rc = self.L.kvhost_get_metrics(self.h, C.byref(m))
+        if rc:
+            raise _native.KvidxError(rc, self.err())
+        d = {k: getattr(m, k) for k, _ in HostMetrics._fields_ if k != "lookup_latency_bucket"}
+        d["lookup_latency_bucket"] = list(m.lookup_latency_bucket)
+        return d
+
+    def metrics_text(self):
+        n = self.L.kvhost_metrics_text(self.h, None, 0)
+        buf = C.create_string_buffer(int(n) + 1)
+        self.L.kvhost_metrics_text(self.h, buf, len(buf))
+        return buf.value.decode()
 
     def add_task(self, pod, model, payload: bytes):
         return self.L.kvhost_pool_add_task(self.h, pod.encode(), model.encode(), payload, len(payload))

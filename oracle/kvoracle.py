@@ -319,6 +319,60 @@ class LongestPrefixScorer:
 
 
 # --------------------------------------------------------------------------
+# metrics: InstrumentedIndex (kvblock/instrumented_index.go:35-92) over the collectors of metrics/collector.go:28-59
+# --------------------------------------------------------------------------
+LATENCY_BUCKETS = (0.005, 0.01, 0.025, 0.05, 0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0)    # prometheus.DefBuckets
+
+
+@dataclass
+class IndexMetrics:
+    admissions_total: int = 0            # kvcache_index_admissions_total
+    evictions_total: int = 0             # kvcache_index_evictions_total
+    lookup_requests_total: int = 0       # kvcache_index_lookup_requests_total
+    max_pod_hit_count_total: int = 0     # kvcache_index_max_pod_hit_count_total
+    lookup_hits_total: int = 0           # kvcache_index_lookup_hits_total
+    lookup_latency_count: int = 0        # kvcache_index_lookup_latency_seconds (count only: values are wall clock)
+
+
+class InstrumentedIndex:
+    """NewInstrumentedIndex (instrumented_index.go:30-92): counts around the wrapped index."""
+
+    def __init__(self, nxt: "InMemoryIndex", metrics: Optional[IndexMetrics] = None):
+        self.next = nxt
+        self.metrics = metrics if metrics is not None else IndexMetrics()
+        self.data = nxt.data
+        self.engine_to_request = nxt.engine_to_request
+
+    def add(self, engine_keys, request_keys, entries) -> None:
+        try:
+            self.next.add(engine_keys, request_keys, entries)
+        finally:
+            self.metrics.admissions_total += len(request_keys)          # :35-39 counted whatever Add returned
+
+    def evict(self, engine_key, entries) -> None:
+        try:
+            self.next.evict(engine_key, entries)
+        finally:
+            self.metrics.evictions_total += len(entries)                # :41-45
+
+    def get_request_key(self, engine_key):
+        return self.next.get_request_key(engine_key)
+
+    def lookup(self, request_keys, pod_filter=()):
+        self.metrics.lookup_latency_count += 1                          # :52-53 timer observed on every return
+        self.metrics.lookup_requests_total += 1                         # :55
+        pods = self.next.lookup(request_keys, pod_filter)               # an error returns before the hit metrics (:57-60)
+        count: Dict[str, int] = {}
+        for entries in pods.values():                                   # recordHitMetrics :71-92
+            for e in entries:
+                count[e.pod] = count.get(e.pod, 0) + 1
+        mx = max(count.values()) if count else 0
+        self.metrics.max_pod_hit_count_total += mx
+        self.metrics.lookup_hits_total += mx
+        return pods
+
+
+# --------------------------------------------------------------------------
 # kvcache.Indexer (steps 2-4 of GetPodScores; tokenisation is out of path)
 # --------------------------------------------------------------------------
 class Indexer:

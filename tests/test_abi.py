@@ -46,6 +46,22 @@ def test_host_mirror_symbols_exported_and_bound():
     assert ei.value.code == kvidx.ECUDA and "no CPU fallback" in str(ei.value)
 
 
+def test_host_metrics_exposition_format():
+    """kvhost_metrics_text: Prometheus text format with the reference's metric names (metrics/collector.go:28-59)."""
+    from kvidx import host
+    h = host.HostIndexer(no_device=True, enable_metrics=True)
+    m = h.metrics()
+    assert m["admissions_total"] == 0 and m["lookup_latency_count"] == 0 and len(m["lookup_latency_bucket"]) == 11
+    text = h.metrics_text()
+    for name in ("admissions_total", "evictions_total", "lookup_requests_total", "max_pod_hit_count_total", "lookup_hits_total"):
+        assert "# TYPE kvcache_index_%s counter\nkvcache_index_%s 0\n" % (name, name) in text
+    assert "# TYPE kvcache_index_lookup_latency_seconds histogram" in text
+    les = re.findall(r'kvcache_index_lookup_latency_seconds_bucket\{le="([^"]+)"\} 0', text)
+    assert les == ["0.005", "0.01", "0.025", "0.05", "0.1", "0.25", "0.5", "1", "2.5", "5", "10", "+Inf"]
+    assert text.endswith("kvcache_index_lookup_latency_seconds_count 0\n")
+    assert C.sizeof(host.HostMetrics) == 8 * (5 + 11 + 1) + 8
+
+
 def test_abi_version_and_struct_layout():
     L = kvidx.load()
     assert L.kvidx_abi_version() == 1

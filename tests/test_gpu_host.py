@@ -58,3 +58,54 @@ def test_pool_and_indexer_strings_end_to_end():
     assert h.evict("other-model", 2 ** 40 + 1, [("pod-a", "gpu"), ("pod-b", "cpu")]) == 0
     assert h.lookup("other-model", [2 ** 41 + 7])[1] == {}
     assert h.get_pod_scores([1, 2, 3], model) is None                    # (nil, nil): no full block
+
+
+def test_metrics_match_the_instrumented_index():
+    """kvcache_index_* counters of the host mirror (enable_metrics) against the oracle's InstrumentedIndex fed with the same
+    events, GetPodScores calls and Index calls (kvblock/instrumented_index.go:35-92)."""
+    sc = golden("scenario_small.json")
+    tiers = [(t, sc["weights"].get(t, 1.0)) for t in ("gpu", "cpu")]
+    h = HostIndexer(block_size=sc["block_size"], hash_seed=sc["hash_seed"], capacity=4096, pods_per_key=sc["pod_cache_size"], tiers=tiers, max_pods=64,
+                    enable_metrics=True)
+    ix = ko.Indexer(block_size=sc["block_size"], hash_seed=sc["hash_seed"], size=10 ** 6, pod_cache_size=sc["pod_cache_size"], weights=sc["weights"])
+    ix.index = ko.InstrumentedIndex(ix.index)
+    pool = ko.EventsPool(ix.index, ix.tokens_processor)
+    model = sc["model"]
+    for i, e in enumerate(sc["events"]):
+        if e["type"] == "BlockStored":
+            body = ["BlockStored", e["hashes"], e["parent"], e["tokens"], sc["block_size"], None, e["medium"]]
+        elif e["type"] == "BlockRemoved":
+            body = ["BlockRemoved", e["hashes"], e["medium"]]
+        else:
+            body = ["AllBlocksCleared"]
+        payload = msgpack.packb([1700000000.0 + i, [body], 0])
+        pool.process_event(e["pod"], model, payload)
+        assert h.add_task(e["pod"], model, payload) == 0
+        if i % 3 == 2:
+            h.process()
+    h.process()
+    for p in sc["prompts"]:
+        assert h.get_pod_scores(p["tokens"], model, p["filter"]) == ix.get_pod_scores(p["tokens"], model, p["filter"])
+    longest = max(sc["prompts"], key=lambda p: len(p["tokens"]))["tokens"]
+    keys = [k.chunk_hash for k in ix.tokens_processor.tokens_to_kv_block_keys(None, longest, model)]
+    uk = list(dict.fromkeys(keys))
+    assert uk
+    h.lookup(model, uk); ix.index.lookup([ko.Key(model, x) for x in uk])
+    h.lookup(model, uk, ["no-such-pod"]); ix.index.lookup([ko.Key(model, x) for x in uk], {"no-such-pod"})
+    assert h.lookup(model, [])[0] == -22
+    with pytest.raises(ko.IndexError_):
+        ix.index.lookup([])
+    assert h.add(model, [1, 2], [3], [("p", "gpu")]) == -22
+    with pytest.raises(ko.IndexError_):
+        ix.index.add([ko.Key(model, 1), ko.Key(model, 2)], [ko.Key(model, 3)], [ko.PodEntry("p", "gpu")])
+    assert h.evict(model, 777, [("p", "gpu"), ("q", "cpu")]) == 0
+    ix.index.evict(ko.Key(model, 777), [ko.PodEntry("p", "gpu"), ko.PodEntry("q", "cpu")])
+    got, want = h.metrics(), ix.index.metrics
+    assert want.admissions_total > 0 and want.evictions_total > 0 and want.max_pod_hit_count_total > 0
+    for name in ("admissions_total", "evictions_total", "lookup_requests_total", "max_pod_hit_count_total", "lookup_hits_total", "lookup_latency_count"):
+        assert got[name] == getattr(want, name), (name, got[name], getattr(want, name))
+    assert got["lookup_latency_bucket"][-1] <= got["lookup_latency_count"] and got["lookup_latency_sum"] > 0
+    assert "kvcache_index_lookup_requests_total %d\n" % want.lookup_requests_total in h.metrics_text()
+    plain = HostIndexer(block_size=sc["block_size"], capacity=1024, max_pods=64)           # metrics off: nothing is counted
+    plain.add(model, [1], [2], [("p", "gpu")]); plain.lookup(model, [2])
+    assert plain.metrics()["admissions_total"] == 0 and plain.metrics()["lookup_requests_total"] == 0

@@ -210,3 +210,28 @@ def test_queue_sharding():                                   # kvevents/pool.go:
     pool = ko.EventsPool(ko.InMemoryIndex(), ko.ChunkedTokenDatabase(), concurrency=4)
     assert pool.queue_index("pod-1") == ko.fnv32a(b"pod-1") % 4
     assert len({pool.queue_index("pod-%d" % i) for i in range(64)}) == 4
+
+
+def test_instrumented_index_counts():
+    """InstrumentedIndex (kvblock/instrumented_index.go:35-92): admissions = len(requestKeys) per Add (also when Add fails),
+    evictions = len(entries) per Evict, one request per Lookup, hits = max over pods of that pod's entries in the result."""
+    ix = ko.InstrumentedIndex(ko.InMemoryIndex(size=100, pod_cache_size=10))
+    m = ix.metrics
+    k = [ko.Key("m", h) for h in (11, 12, 13)]
+    e = [ko.Key("m", h) for h in (21, 22, 23)]
+    ix.add(e, k, [ko.PodEntry("a", "gpu"), ko.PodEntry("b", "gpu")])
+    ix.add(e[:2], k[:2], [ko.PodEntry("a", "cpu")])                     # pod a on two tiers of keys 11, 12
+    assert m.admissions_total == 5
+    with pytest.raises(ko.IndexError_):
+        ix.add(e[:2], k[:1], [ko.PodEntry("a", "gpu")])                 # length mismatch: still counted (len(requestKeys) = 1)
+    assert m.admissions_total == 6
+    hits = ix.lookup(k + [ko.Key("m", 99)])                             # a: 2 + 2 + 1 entries, b: 3
+    assert len(hits) == 3 and (m.lookup_requests_total, m.max_pod_hit_count_total, m.lookup_hits_total, m.lookup_latency_count) == (1, 5, 5, 1)
+    ix.lookup(k, {"b"})
+    assert (m.lookup_requests_total, m.max_pod_hit_count_total) == (2, 8)
+    with pytest.raises(ko.IndexError_):
+        ix.lookup([])                                                   # an error: request and latency counted, no hits
+    assert (m.lookup_requests_total, m.lookup_latency_count, m.lookup_hits_total) == (3, 3, 8)
+    ix.evict(e[0], [ko.PodEntry("a", "gpu"), ko.PodEntry("a", "cpu")])
+    ix.evict(ko.Key("m", 404), [ko.PodEntry("a", "gpu")])               # unknown engine key: silent no-op, still counted
+    assert m.evictions_total == 3
