@@ -12,6 +12,7 @@
  *   kvhost_pool_add_task     <-> kvevents.Pool.AddTask                pkg/kvcache/kvevents/pool.go:132-144
  *   kvhost_pool_process      <-> worker loop: processEvent + digestEvents       pkg/kvcache/kvevents/pool.go:149-338
  *   kvhost_decode_event_batch<-> processEvent's msgpack decoding      pkg/kvcache/kvevents/pool.go:177-244, events.go:38-96
+ *   kvhost_prefix_store_*    <-> prefixstore.LRUTokenStore            pkg/tokenization/prefixstore/lru_store.go:54-190
  *   kvhost_get_metrics / _text <-> InstrumentedIndex + collectors      pkg/kvcache/kvblock/instrumented_index.go:30-92, metrics/collector.go:28-59
  */
 #ifndef KVIDX_HOST_H
@@ -89,6 +90,27 @@ int kvhost_get_metrics(kvhost_t* h, kvhost_metrics_t* out);
 /* Prometheus text exposition of the above (same metric names and help strings as the reference).  Returns the number of
  * bytes needed (excluding the NUL); writes at most cap - 1 bytes + NUL. */
 int64_t kvhost_metrics_text(kvhost_t* h, char* buf, size_t cap);
+
+/* Tokenization prefix store (the cache in front of the tokenizer; the tokenizer itself stays with the
+ * embedding program).  Text is cut into block_size-BYTE blocks, block i is keyed by XXH64(seed 0) of the little-endian
+ * previous key followed by the block's bytes (lru_store.go:111-121), and maps to the tokens whose END offset falls inside
+ * the text up to the block's end (:124-137).  A partial last block is never stored or looked up.
+ *   create: NewLRUTokenStore (:72-87); cache_size <= 0 is an error like lru.New; defaults 500000 blocks of 256 bytes.
+ *   add:    AddTokenization (:89-141); offsets are n_tokens pairs [low, high) of byte offsets; empty prompt or no
+ *           tokens is a no-op.
+ *   find:   FindLongestContainedTokens (:143-190): walks the blocks until the first one missing from the cache (a hit
+ *           refreshes its recency); returns the number of contained tokens (all of them are written if cap allows, else
+ *           the first cap) and the covered fraction of the prompt, end of the last matched block / prompt length.
+ * tokenization.Pool.processTask (pool.go:209-225) is: find; if the ratio is below 0.8 tokenize, add, use the fresh tokens. */
+typedef struct kvhost_prefix_store kvhost_prefix_store_t;
+int  kvhost_prefix_store_create(int64_t cache_size, int32_t block_size, kvhost_prefix_store_t** out);
+void kvhost_prefix_store_destroy(kvhost_prefix_store_t* s);
+int  kvhost_prefix_store_add(kvhost_prefix_store_t* s, const char* prompt, size_t prompt_len, const uint32_t* tokens,
+                             const uint64_t* offsets, size_t n_tokens);
+int64_t kvhost_prefix_store_find(kvhost_prefix_store_t* s, const char* prompt, size_t prompt_len, uint32_t* tokens_out, size_t cap,
+                                 double* overlap_ratio_out);
+int64_t kvhost_prefix_store_len(kvhost_prefix_store_t* s);           /* blocks resident */
+uint64_t kvhost_xxhash64(const void* data, size_t len, uint64_t seed);
 
 /* interning introspection (ids are append-only and never reused) */
 int kvhost_pod_id(kvhost_t* h, const char* pod);

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <chrono>
 #include <deque>
+#include <list>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -507,6 +508,113 @@ int64_t kvhost_decode_event_batch(kvhost_t* h, const char* pod, const char* mode
     if (n_hash_out) *n_hash_out = hashes.size();
     if (n_tok_out) *n_tok_out = toks.size();
     return (int64_t)evs.size();
+}
+
+}  // extern "C"
+
+// ---- tokenization prefix store (prefixstore/lru_store.go) -------------------------------------------------------------
+namespace {
+constexpr uint64_t XP1 = 0x9E3779B185EBCA87ull, XP2 = 0xC2B2AE3D27D4EB4Full, XP3 = 0x165667B19E3779F9ull, XP4 = 0x85EBCA77C2B2AE63ull,
+                   XP5 = 0x27D4EB2F165667C5ull;
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }      // little-endian hosts only (x86-64, aarch64)
+inline uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint64_t xx_round(uint64_t acc, uint64_t in) { return rotl64(acc + in * XP2, 31) * XP1; }
+inline uint64_t xx_merge(uint64_t h, uint64_t v) { return (h ^ xx_round(0, v)) * XP1 + XP4; }
+
+// XXH64 as published (cespare/xxhash/v2 in the reference's go.mod); fed in two pieces (the 8-byte chain prefix, then the block)
+uint64_t xxh64(const uint8_t* p, size_t n, uint64_t seed) {
+    const uint8_t* e = p + n;
+    uint64_t h;
+    if (n >= 32) {
+        uint64_t v1 = seed + XP1 + XP2, v2 = seed + XP2, v3 = seed, v4 = seed - XP1;
+        for (; p + 32 <= e; p += 32) { v1 = xx_round(v1, rd64(p)); v2 = xx_round(v2, rd64(p + 8)); v3 = xx_round(v3, rd64(p + 16)); v4 = xx_round(v4, rd64(p + 24)); }
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = xx_merge(h, v1); h = xx_merge(h, v2); h = xx_merge(h, v3); h = xx_merge(h, v4);
+    } else h = seed + XP5;
+    h += (uint64_t)n;
+    for (; p + 8 <= e; p += 8) h = rotl64(h ^ xx_round(0, rd64(p)), 27) * XP1 + XP4;
+    if (p + 4 <= e) { h = rotl64(h ^ ((uint64_t)rd32(p) * XP1), 23) * XP2 + XP3; p += 4; }
+    for (; p < e; ++p) h = rotl64(h ^ ((uint64_t)*p * XP5), 11) * XP1;
+    h ^= h >> 33; h *= XP2; h ^= h >> 29; h *= XP3; h ^= h >> 32;
+    return h;
+}
+}  // namespace
+
+struct kvhost_prefix_store {
+    int64_t cache_size; int32_t block_size;
+    std::mutex mu;
+    // golang-lru semantics: Add inserts at the front (or updates and refreshes), evicts the back beyond cache_size; Get refreshes
+    std::list<std::pair<uint64_t, std::vector<uint32_t>>> order;
+    std::unordered_map<uint64_t, std::list<std::pair<uint64_t, std::vector<uint32_t>>>::iterator> map;
+    std::vector<uint8_t> scratch;
+
+    uint64_t chain(uint64_t prev, const uint8_t* blk) {
+        scratch.resize(8 + (size_t)block_size);
+        memcpy(scratch.data(), &prev, 8);
+        memcpy(scratch.data() + 8, blk, (size_t)block_size);
+        return xxh64(scratch.data(), scratch.size(), 0);
+    }
+};
+
+extern "C" {
+
+uint64_t kvhost_xxhash64(const void* data, size_t len, uint64_t seed) { return xxh64((const uint8_t*)data, len, seed); }
+
+int kvhost_prefix_store_create(int64_t cache_size, int32_t block_size, kvhost_prefix_store_t** out) {
+    if (!out) return hfail(KVIDX_EINVAL, "bad arguments");
+    if (cache_size <= 0) return hfail(KVIDX_EINVAL, "failed to initialize in-memory index: must provide a positive size");     // lru.New
+    if (block_size <= 0) return hfail(KVIDX_EINVAL, "block size must be positive");
+    auto* s = new kvhost_prefix_store();
+    s->cache_size = cache_size; s->block_size = block_size;
+    *out = s;
+    return 0;
+}
+
+void kvhost_prefix_store_destroy(kvhost_prefix_store_t* s) { delete s; }
+
+int64_t kvhost_prefix_store_len(kvhost_prefix_store_t* s) { if (!s) return KVIDX_EINVAL; std::lock_guard<std::mutex> g(s->mu); return (int64_t)s->map.size(); }
+
+int kvhost_prefix_store_add(kvhost_prefix_store_t* s, const char* prompt, size_t prompt_len, const uint32_t* tokens, const uint64_t* offsets, size_t n_tokens) {
+    if (!s || (prompt_len && !prompt) || (n_tokens && (!tokens || !offsets))) return hfail(KVIDX_EINVAL, "bad arguments");
+    if (prompt_len == 0 || n_tokens == 0) return 0;                                  // lru_store.go:96-98
+    std::lock_guard<std::mutex> g(s->mu);
+    const size_t bs = (size_t)s->block_size;
+    size_t it = 0;
+    uint64_t prev = 0;
+    for (size_t start = 0; start + bs <= prompt_len; start += bs) {                  // no partial blocks
+        const size_t end = start + bs;
+        prev = s->chain(prev, (const uint8_t*)prompt + start);
+        std::vector<uint32_t> blk;
+        for (; it < n_tokens && offsets[2 * it + 1] <= end; ++it) blk.push_back(tokens[it]);      // a token goes with the block its END falls in
+        auto f = s->map.find(prev);
+        if (f != s->map.end()) { f->second->second = std::move(blk); s->order.splice(s->order.begin(), s->order, f->second); }
+        else {
+            s->order.emplace_front(prev, std::move(blk));
+            s->map[prev] = s->order.begin();
+            if ((int64_t)s->map.size() > s->cache_size) { s->map.erase(s->order.back().first); s->order.pop_back(); }
+        }
+    }
+    return 0;
+}
+
+int64_t kvhost_prefix_store_find(kvhost_prefix_store_t* s, const char* prompt, size_t prompt_len, uint32_t* tokens_out, size_t cap, double* ratio_out) {
+    if (!s || (prompt_len && !prompt)) return hfail(KVIDX_EINVAL, "bad arguments");
+    std::lock_guard<std::mutex> g(s->mu);
+    const size_t bs = (size_t)s->block_size;
+    uint64_t prev = 0;
+    double ratio = 0.0;
+    int64_t n = 0;
+    for (size_t i = 0; i + bs <= prompt_len; i += bs) {
+        prev = s->chain(prev, (const uint8_t*)prompt + i);
+        auto f = s->map.find(prev);
+        if (f == s->map.end()) break;                                                // early stop
+        s->order.splice(s->order.begin(), s->order, f->second);                      // Get refreshes recency
+        for (uint32_t t : f->second->second) { if (tokens_out && (size_t)n < cap) tokens_out[n] = t; ++n; }
+        ratio = (double)(i + bs) / (double)prompt_len;
+    }
+    if (ratio_out) *ratio_out = ratio;
+    return n;
 }
 
 }  // extern "C"

@@ -32,6 +32,12 @@ SYMBOLS = {
     "kvhost_config_default": (None, [C.POINTER(HostConfig)]),
     "kvhost_create": (C.c_int, [C.POINTER(HostConfig), C.c_char_p, C.POINTER(C.c_void_p)]),
     "kvhost_destroy": (None, [C.c_void_p]),
+    "kvhost_prefix_store_create": (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]),
+    "kvhost_prefix_store_destroy": (None, [C.c_void_p]),
+    "kvhost_prefix_store_add": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "kvhost_prefix_store_find": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_double)]),
+    "kvhost_prefix_store_len": (C.c_int64, [C.c_void_p]),
+    "kvhost_xxhash64": (C.c_uint64, [C.c_char_p, C.c_size_t, C.c_uint64]),
     "kvhost_get_metrics": (C.c_int, [C.c_void_p, C.POINTER(HostMetrics)]),
     "kvhost_metrics_text": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_size_t]),
     "kvhost_last_error": (C.c_char_p, []),
@@ -181,3 +187,48 @@ class HostIndexer:
 
     def tier_id(self, s):
         return self.L.kvhost_tier_id(self.h, s.encode("utf-8", "surrogateescape"))
+
+
+def xxhash64(data: bytes, seed: int = 0) -> int:
+    return int(_lib().kvhost_xxhash64(data, len(data), seed))
+
+
+class PrefixStore:
+    """prefixstore.LRUTokenStore (the cache in front of the tokenizer): text blocks -> the tokens that end inside them."""
+
+    def __init__(self, cache_size=500000, block_size=256):
+        self.L = _lib()
+        h = C.c_void_p()
+        rc = self.L.kvhost_prefix_store_create(cache_size, block_size, C.byref(h))
+        if rc:
+            raise _native.KvidxError(rc, self.L.kvhost_last_error().decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kvhost_prefix_store_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(self.L.kvhost_prefix_store_len(self.h))
+
+    def add_tokenization(self, prompt: bytes, tokens, offsets):
+        tok = np.ascontiguousarray(tokens, np.uint32)
+        off = np.ascontiguousarray(offsets, np.uint64).reshape(-1, 2) if len(tok) else np.zeros((0, 2), np.uint64)
+        assert len(off) == len(tok)
+        rc = self.L.kvhost_prefix_store_add(self.h, prompt, len(prompt), tok.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(tok))
+        if rc:
+            raise _native.KvidxError(rc, self.L.kvhost_last_error().decode())
+
+    def find_longest_contained_tokens(self, prompt: bytes):
+        ratio = C.c_double(0.0)
+        n = self.L.kvhost_prefix_store_find(self.h, prompt, len(prompt), None, 0, C.byref(ratio))      # count only (and refresh)
+        out = np.zeros(max(int(n), 1), np.uint32)
+        n = self.L.kvhost_prefix_store_find(self.h, prompt, len(prompt), out.ctypes.data_as(C.c_void_p), len(out), C.byref(ratio))
+        return out[: int(n)].tolist(), ratio.value

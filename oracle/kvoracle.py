@@ -319,6 +319,112 @@ class LongestPrefixScorer:
 
 
 # --------------------------------------------------------------------------
+# tokenization prefix store (pkg/tokenization/prefixstore/lru_store.go): the cache in front of the tokenizer
+# --------------------------------------------------------------------------
+_XP1, _XP2, _XP3 = 0x9E3779B185EBCA87, 0xC2B2AE3D27D4EB4F, 0x165667B19E3779F9
+_XP4, _XP5 = 0x85EBCA77C2B2AE63, 0x27D4EB2F165667C5
+
+
+def _rotl64(x: int, r: int) -> int:
+    return ((x << r) | (x >> (64 - r))) & MASK64
+
+
+def _xx_round(acc: int, inp: int) -> int:
+    return (_rotl64((acc + inp * _XP2) & MASK64, 31) * _XP1) & MASK64
+
+
+def _xx_merge(h: int, v: int) -> int:
+    return (((h ^ _xx_round(0, v)) * _XP1) + _XP4) & MASK64
+
+
+def xxhash64(data: bytes, seed: int = 0) -> int:
+    """XXH64 (github.com/cespare/xxhash/v2 v2.3.0 in the reference's go.mod; algorithm: the published xxHash spec)."""
+    n, i = len(data), 0
+    if n >= 32:
+        v1, v2, v3, v4 = (seed + _XP1 + _XP2) & MASK64, (seed + _XP2) & MASK64, seed, (seed - _XP1) & MASK64
+        while i + 32 <= n:
+            v1 = _xx_round(v1, int.from_bytes(data[i:i + 8], "little")); v2 = _xx_round(v2, int.from_bytes(data[i + 8:i + 16], "little"))
+            v3 = _xx_round(v3, int.from_bytes(data[i + 16:i + 24], "little")); v4 = _xx_round(v4, int.from_bytes(data[i + 24:i + 32], "little"))
+            i += 32
+        h = (_rotl64(v1, 1) + _rotl64(v2, 7) + _rotl64(v3, 12) + _rotl64(v4, 18)) & MASK64
+        for v in (v1, v2, v3, v4):
+            h = _xx_merge(h, v)
+    else:
+        h = (seed + _XP5) & MASK64
+    h = (h + n) & MASK64
+    while i + 8 <= n:
+        h = (_rotl64(h ^ _xx_round(0, int.from_bytes(data[i:i + 8], "little")), 27) * _XP1 + _XP4) & MASK64
+        i += 8
+    if i + 4 <= n:
+        h = (_rotl64(h ^ (int.from_bytes(data[i:i + 4], "little") * _XP1 & MASK64), 23) * _XP2 + _XP3) & MASK64
+        i += 4
+    while i < n:
+        h = (_rotl64(h ^ (data[i] * _XP5 & MASK64), 11) * _XP1) & MASK64
+        i += 1
+    h ^= h >> 33; h = (h * _XP2) & MASK64
+    h ^= h >> 29; h = (h * _XP3) & MASK64
+    h ^= h >> 32
+    return h
+
+
+PREFIX_STORE_BLOCK_SIZE = 256        # lru_store.go:29 (bytes of text per block, despite the field's comment)
+PREFIX_STORE_CACHE_SIZE = 500000     # lru_store.go:31
+
+
+class LRUTokenStore:
+    """prefixstore.LRUTokenStore (lru_store.go:54-190): xxhash64-chained text blocks -> the tokens that end inside them."""
+
+    def __init__(self, cache_size: int = PREFIX_STORE_CACHE_SIZE, block_size: int = PREFIX_STORE_BLOCK_SIZE):
+        self.block_size = block_size
+        self.cache = LRU(cache_size)
+
+    def _hash(self, prev: int, chunk: bytes) -> int:
+        return xxhash64(prev.to_bytes(8, "little") + chunk)              # :111-118 binary.Write(LE, previousHash) then the chunk
+
+    def add_tokenization(self, prompt: bytes, tokens: Sequence[int], offsets: Sequence[Tuple[int, int]]) -> None:
+        """AddTokenization (:89-141).  prompt is the UTF-8 byte string; offsets are byte offsets [low, high)."""
+        if len(prompt) == 0 or len(tokens) == 0:
+            return
+        it, prev = 0, 0
+        for start in range(0, len(prompt), self.block_size):
+            end = start + self.block_size
+            if end > len(prompt):
+                break                                                    # no partial blocks
+            prev = self._hash(prev, prompt[start:end])
+            blk = []
+            while it < len(tokens) and offsets[it][1] <= end:            # :128-135 a token belongs to the block its END falls in
+                blk.append(tokens[it]); it += 1
+            self.cache.add(prev, blk)
+
+    def find_longest_contained_tokens(self, prompt: bytes) -> Tuple[List[int], float]:
+        """FindLongestContainedTokens (:143-190)."""
+        out: List[int] = []
+        prev, ratio = 0, 0.0
+        for i in range(0, len(prompt), self.block_size):
+            end = i + self.block_size
+            if end > len(prompt):
+                break
+            prev = self._hash(prev, prompt[i:end])
+            blk, ok = self.cache.get(prev)                               # refreshes recency
+            if not ok:
+                break                                                    # early stop
+            out.extend(blk)
+            ratio = end / len(prompt)
+        return out, ratio
+
+
+def tokenize_with_prefix_store(store: LRUTokenStore, prompt: bytes, encode, min_overlap: float = 0.8) -> List[int]:
+    """tokenization.Pool.processTask after chat templating (pool.go:209-225): reuse the contained tokens when the cached
+    prefix covers at least min_overlap of the prompt, else tokenize and remember.  encode(prompt) -> (tokens, offsets)."""
+    toks, ratio = store.find_longest_contained_tokens(prompt)
+    if ratio < min_overlap:
+        tokens, offsets = encode(prompt)
+        store.add_tokenization(prompt, tokens, offsets)
+        return list(tokens)
+    return toks
+
+
+# --------------------------------------------------------------------------
 # metrics: InstrumentedIndex (kvblock/instrumented_index.go:35-92) over the collectors of metrics/collector.go:28-59
 # --------------------------------------------------------------------------
 LATENCY_BUCKETS = (0.005, 0.01, 0.025, 0.05, 0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0)    # prometheus.DefBuckets

@@ -192,9 +192,26 @@ def scenario_small():
             "final_request_keys": len(ix.index.data), "final_engine_keys": len(ix.index.engine_to_request)}
 
 
+def prefix_store_kats():
+    """XXH64 vectors and chained block keys of the reference's prefix-store test text (lru_store_test.go:36-44), computed with
+    the xxhash package (C library binding) -- independent of oracle/ and of the C++ host layer."""
+    import xxhash
+    vec = [b"", b"a", b"abc", b"The capital of France is Paris", bytes(range(256)), b"x" * 31, b"y" * 32, b"z" * 33, bytes(range(97, 123)) * 11]
+    kats = [{"hex": v.hex(), "seed": sd, "xxh64": xxhash.xxh64(v, seed=sd).intdigest()} for v in vec for sd in (0, 1, 0x9E3779B97F4A7C15)]
+    text = b"The capital of France is Paris"
+    chains = {}
+    for bs in (4, 8, 30):
+        prev, keys = 0, []
+        for st in range(0, len(text) - bs + 1, bs):
+            prev = xxhash.xxh64(prev.to_bytes(8, "little") + text[st:st + bs], seed=0).intdigest()
+            keys.append(prev)
+        chains[str(bs)] = keys
+    return {"xxh64": kats, "text": text.decode(), "block_keys": chains}
+
+
 def main():
     for name, fn in (("hash_kats.json", hash_kats), ("kv_event_base_keys.json", kv_event_base),
-                     ("scenario_small.json", scenario_small)):
+                     ("scenario_small.json", scenario_small), ("prefix_store_kats.json", prefix_store_kats)):
         with open(os.path.join(HERE, name), "w") as f:
             json.dump(fn(), f, separators=(",", ":"))
         print("wrote", name, os.path.getsize(os.path.join(HERE, name)), "bytes")
