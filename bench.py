@@ -272,11 +272,14 @@ def run_ours(args):
         ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + (1 << 20), max_pods=wl.P, tier_weights=WEIGHTS, device=local)
     t0 = time.time()
     n_ev = 0
+    apply_s = 0.0                                    # time inside kvidx_apply_events (host arrays in, H2D + kernel), generation excluded
     for d0 in range(0, wl.D, 4096):
         ev, hs, tk = wl.fill_events(d0, min(wl.D, d0 + 4096))
         if mode == "sharded":
             ev = kd.events_for_rank(ev, rank, world)
+        ta = time.perf_counter()
         rc, dropped = ix.apply_events(ev, hs, tk)
+        apply_s += time.perf_counter() - ta
         assert rc == 0 and dropped == 0, (rc, dropped, ix.last_error())
         n_ev += len(ev)
     barrier()
@@ -480,6 +483,10 @@ def run_ours(args):
                           "multi_gpu": {"single": "single GPU", "replicas": "replicas: full index per GPU, prompts sharded, no data-path collective",
                                         "sharded": "hash-range sharded tables, probes over NVLink peer memory (CUDA IPC), per-pod ingest ranks"}[mode],
                           "index_fill_s": fill_s, "fill_events": n_ev},
+               "write_path": {"apply_events_s": apply_s, "events_per_s": n_ev / apply_s, "blocks_per_s": st["request_keys"] / apply_s,
+                              "algorithmic_GBps": st["request_keys"] * 136 / apply_s / 1e9,
+                              "note": "index fill through kvidx_apply_events from host arrays (BlockStored, %d blocks per event): copy in + "
+                                      "apply_events_kernel; A_ev = 136 B per block (SURVEY 8(d))" % wl.bpe},
                "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k, "value_at_512k_batch": value_512k, "mixed_read_write": mixed,
                "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         emit(out)
