@@ -33,8 +33,12 @@ for p in (ROOT, PKG):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-T_TOKENS, N_BLOCKS, N_PODS, BLOCK = 4096, 10_000_000, 256, 16
-CONFIG_ID = 6          # "metric row" of SURVEY 8(d): T=4K, N=10M, P=256
+# "metric row" of SURVEY 8(d): T=4K, N=10M, P=256.  The other BASELINE configs run through the same script:
+#   #3  KVIDX_BENCH_TOKENS=8192                      #4  KVIDX_BENCH_BLOCKS=100000000 KVIDX_BENCH_MODE=sharded --gpus 8
+T_TOKENS = int(os.environ.get("KVIDX_BENCH_TOKENS", "4096"))
+N_BLOCKS = int(os.environ.get("KVIDX_BENCH_BLOCKS", "10000000"))
+N_PODS, BLOCK = 256, 16
+CONFIG_ID = 6
 WEIGHTS = (1.0, 0.8)
 
 
@@ -220,7 +224,8 @@ def run_reference(args):
     out = {"metric": "score_prompts_per_sec", "value": value, "unit": "prompts/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "impl": "reference",
-           "config": {"workload": "Score() 4096-token prompts, 10M-block / 256-pod index (SURVEY 8(d) metric row)",
+           "config": {"workload": "Score() %d-token prompts, %s-block / 256-pod index (SURVEY 8(d) %s)" % (
+                              T_TOKENS, "%dM" % round(N_BLOCKS / 1e6), "metric row" if (T_TOKENS, N_BLOCKS) == (4096, 10_000_000) else "config variant"),
                       "prompt_tokens": wl.T, "index_blocks": wl.n_blocks, "pods": wl.P, "block_size": BLOCK,
                       "batch_prompts": sample, "query_mix": "m uniform in [0,n] matched blocks + random tail"},
            "cpu_baseline": {"value": value, "unit": "prompts/s", "cores": threads, "kind": "port",
@@ -473,7 +478,8 @@ def run_ours(args):
         out = {"metric": "score_prompts_per_sec", "value": value, "unit": "prompts/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-               "config": {"workload": "Score() 4096-token prompts, 10M-block / 256-pod index (SURVEY 8(d) metric row)",
+               "config": {"workload": "Score() %d-token prompts, %s-block / 256-pod index (SURVEY 8(d) %s)" % (
+                              T_TOKENS, "%dM" % round(N_BLOCKS / 1e6), "metric row" if (T_TOKENS, N_BLOCKS) == (4096, 10_000_000) else "config variant"),
                           "prompt_tokens": wl.T, "index_blocks": wl.n_blocks, "pods": wl.P, "block_size": BLOCK,
                           "batch_prompts_per_gpu": Q, "query_mix": "m uniform in [0,n] matched blocks + random tail",
                           "queries_per_document": Q / wl.D,
