@@ -952,6 +952,14 @@ __global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsig
     if (i == 0) for (int q = 0; q < kMaxParts; ++q) { cnt[8 * q] = ps.n[q]; cnt[8 * q + 1] = 0; }      // live-list lengths per part
 }
 
+// Distinct values among the sorted fingerprints (the sort orders by the top 32 bits, so those are compared).
+__global__ void count_distinct_prefixes_kernel(const uint64_t* __restrict__ fp_sorted, int64_t n, unsigned long long* out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool edge = i < n && (i == 0 || (fp_sorted[i] >> 32) != (fp_sorted[i - 1] >> 32));
+    const unsigned int m = __ballot_sync(0xffffffffu, edge);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
 inline int rounds_init() {
     if (cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(group_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)) != cudaSuccess) return -1;

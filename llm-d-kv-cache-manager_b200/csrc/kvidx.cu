@@ -100,6 +100,7 @@ struct kvidx {
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
     int64_t classes_min = 393216;  // ... and at least this large, the prefix-class round pipeline
+    double classes_min_sharing = 0.85;   // ... if at least this fraction of the batch follows a representative in round 0
     DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate, r_anch, r_snap, r_rec;
     int64_t host_chunk_tokens = 32ll << 20;   // tokens per H2D chunk of the host-buffer pipeline
     int rounds_trace = 0;
@@ -209,6 +210,10 @@ int enforce_caps(kvidx* x) {
 
 struct ScoreOut { double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* sp_cnt; uint8_t* has_keys; };
 
+int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
+                              const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
+                              int64_t max_blocks);
+
 // Large batches: rounds of group / hash / walk / resolve kernels (kernels_rounds.cuh).  max_blocks < 0: computed on the
 // device.  The sorted batch is split into parts that run their rounds on separate streams, so that one part's
 // latency-bound kernels (the serial FNV chain of few representatives, the dependent probes) share the SMs with
@@ -279,11 +284,24 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         CK(cub::DeviceRadixSort::SortPairs(x->r_sort.p, tmp, fp_in, fp_out, idx_in, rb[0].act[0], (int)n, 32, 64, st));
         x->launches += 5;     // cub: histogram + 4 onesweep passes (the top 32 fingerprint bits order the groups well enough)
     }
-    if (max_blocks < 0) {
-        unsigned long long mb = 0;
-        CK(cudaMemcpyAsync(&mb, d_maxb, sizeof mb, cudaMemcpyDeviceToHost, st));
+    // Is the batch worth it?  The class pipeline pays a token pass and five kernels per round; with few prompts per distinct
+    // prefix (measured crossover: ~6 prompts per cached document) the per-prompt rounds are faster.  The sorted first-block
+    // fingerprints tell before anything is spent: count the distinct ones, and hand the batch over if more than 15 % of the
+    // prompts start differently from their neighbour.  (The device-resident entry point waits for the block count here anyway.)
+    const bool adaptive = x->score_path == 0 && x->rounds_dedup && x->sort_prefix && x->classes_min_sharing > 0.0;
+    if (adaptive) {
+        count_distinct_prefixes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(fp_out, n, d_maxb + 1);
+        x->launches += 1;
+    }
+    if (max_blocks < 0 || adaptive) {
+        unsigned long long mb[2] = {0, 0};
+        CK(cudaMemcpyAsync(mb, d_maxb, sizeof mb, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        max_blocks = (int64_t)mb;
+        if (max_blocks < 0) max_blocks = (int64_t)mb[0];
+        if (adaptive && (double)mb[1] > (1.0 - x->classes_min_sharing) * (double)n) {
+            if (x->rounds_trace) fprintf(stderr, "[kvidx rounds] %llu distinct first blocks among %lld prompts: per-prompt rounds instead\n", mb[1], (long long)n);
+            return launch_score_rounds_plain(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks);
+        }
     }
     int64_t rounds = (max_blocks + kRoundBlocks - 1) / kRoundBlocks;
     if (x->rounds_dedup >= 2) rounds += 1;            // a prompt that left its class mid-chunk runs unaligned from there: one more round
@@ -307,6 +325,10 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
             group_round_kernel<16><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
             const unsigned lgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : x->rounds_grid[1]));
             group_lists_kernel<16><<<lgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2);
+        }
+        for (int q = 0; q < np; ++q) {
+            const int64_t m = psz[q];
+            if (m <= 0) continue;
             const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * (np == 1 ? 4 : x->rounds_grid[2]));
             hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
             const unsigned wgrid = (unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)x->sm_count * (np == 1 ? 8 : x->rounds_grid[3]));
@@ -681,6 +703,7 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : !strcmp(k, "classes") ? 3 : 0;
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
     if (const char* k = getenv("KVIDX_CLASSES_MIN")) x->classes_min = atoll(k);
+    if (const char* k = getenv("KVIDX_CLASSES_SHARING")) x->classes_min_sharing = atof(k);
     if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_GRID")) sscanf(k, "%d,%d,%d,%d,%d", &x->rounds_grid[0], &x->rounds_grid[1], &x->rounds_grid[2], &x->rounds_grid[3], &x->rounds_grid[4]);

@@ -273,6 +273,11 @@ def _select_path(monkeypatch, path):
     if path == "v1":
         monkeypatch.setenv("KVIDX_SCORE_KERNEL", "v1")
         return
+    if path == "auto":                       # the library chooses: here every batch is "large", so it is the class pipeline
+        monkeypatch.setenv("KVIDX_ROUNDS_MIN", "1")        # or the per-prompt rounds, by how much the batch repeats itself
+        monkeypatch.setenv("KVIDX_CLASSES_MIN", "64")
+        monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP_MIN", "64")
+        return
     base, _, var = path.partition("-")
     parts = base.lstrip("abcdefghijklmnopqrstuvwxyz")
     base = base[: len(base) - len(parts)]
@@ -291,7 +296,7 @@ def _select_path(monkeypatch, path):
 
 
 ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "classes", "classes2", "classes8", "classes-nosort", "classes-nodedup", "classes-whole",
-               "classes4-whole"]
+               "classes4-whole", "auto"]
 PATHS = ["v1", "fused"] + ROUND_PATHS
 
 
@@ -502,6 +507,27 @@ def test_tiny_alphabet_fuzz(kernel, seed, monkeypatch):
     s_t, _ = ix.score_batch(tok, off)
     s_o, _, _, _ = co.score_batch(tok, off, n_threads=4)
     assert np.array_equal(s_t, s_o) and (s_t == s_t[0]).all()
+
+
+def test_automatic_fallback_by_sharing(monkeypatch, capfd):
+    """A large batch goes to the class pipeline only if it repeats itself: the sorted first-block fingerprints are counted
+    first.  Unique prompts: per-prompt rounds.  The same prompts repeated 16 times: classes.  Results identical either way."""
+    _select_path(monkeypatch, "auto")
+    monkeypatch.setenv("KVIDX_ROUNDS_TRACE", "2")
+    wl = synth.Workload(9, 512, 1 << 13, 32)
+    ix, co = _index_pair(capacity=1 << 14, max_pods=32)
+    ev, hs, tk = wl.fill_events(0, wl.D)
+    assert ix.apply_events(ev, hs, tk)[0] == 0 and co.apply_events(ev, hs, tk)[0] == 0
+    rng = np.random.default_rng(3)
+    uniq = [rng.integers(0, 50000, size=512, dtype=np.uint32) for _ in range(600)]
+    for batch, fell_back in ((uniq, True), (uniq[:40] * 16, False)):
+        tok, off = csr(batch)
+        capfd.readouterr()
+        s_t, _ = ix.score_batch(tok, off)
+        err = capfd.readouterr().err
+        assert ("per-prompt rounds instead" in err) == fell_back, err
+        s_o, _, _, _ = co.score_batch(tok, off, n_threads=4)
+        assert np.array_equal(s_t, s_o)
 
 
 def test_config5_scores_while_the_write_path_runs():
