@@ -484,7 +484,9 @@ def run_ours(args):
                           "batch_prompts_per_gpu": Q, "query_mix": "m uniform in [0,n] matched blocks + random tail",
                           "queries_per_document": Q / wl.D,
                           "pipeline": "prefix-class rounds: each distinct prefix is hashed and probed once per batch (batches >= 393216 prompts; "
-                                      "smaller ones take the per-prompt round or fused kernels)" if Q >= 393216 else "per-prompt rounds",
+                                      "smaller ones, and batches with little repetition, take the per-prompt round or fused kernels)"
+                                      if launches / max(args.steps, 1) > 100 else "per-prompt rounds (batch below the class pipeline's size threshold, or too "
+                                      "little repetition: fewer than ~6 prompts per distinct first block)",
                           "l2_policy": "inputs (%.1f GB tokens + %.1f GB table) larger than the 126 MB L2; no flush" % (Q * wl.T * 4 / 1e9, st["request_slots"] * 32 / 1e9),
                           "multi_gpu": {"single": "single GPU", "replicas": "replicas: full index per GPU, prompts sharded, no data-path collective",
                                         "sharded": "hash-range sharded tables, probes over NVLink peer memory (CUDA IPC), per-pod ingest ranks"}[mode],
