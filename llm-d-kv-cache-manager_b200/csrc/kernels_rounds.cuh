@@ -942,7 +942,12 @@ __global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsig
         if (nb > 0) {
             f = 0x9E3779B97F4A7C15ull;
             const uint32_t* tk = a.tok + b;
-            for (uint32_t j = 0; j < block_size && j < 16u; ++j) f = mix64(f ^ __ldg(tk + j));
+            // (independent mixes of token pairs, not a chain: this kernel is one thread per prompt and latency bound)
+            const uint32_t nt = block_size < 16u ? block_size : 16u;
+            uint64_t g = 0;
+            for (uint32_t j = 0; j + 1 < nt; j += 2) g ^= mix64(((uint64_t)__ldg(tk + j + 1) << 32 | __ldg(tk + j)) + 0xC2B2AE3D27D4EB4Full * (j + 1));
+            if (nt & 1u) g ^= mix64(__ldg(tk + nt - 1) + 0x165667B19E3779F9ull);
+            f = mix64(f ^ g);
             f &= ~(1ull << 63);
         }
         fp[i] = f; idx[i] = (uint32_t)i;
