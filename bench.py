@@ -415,7 +415,7 @@ def run_ours(args):
             "algorithmic_bytes_per_launch": float(A.sum()), "kernel_ms": float(step_ms.mean()),
             "kernel": "one step = prefix sort + 9 rounds x 8 parts x (group_round, group_lists, hash_round, walk_round, finish_round kernels); "
                       "achieved = step's algorithmic bytes / step GPU time (CUDA events around all of its launches), i.e. a lower bound for "
-                      "every kernel in it; group_round_kernel (token streaming, 31 % of the step) alone runs at 69 % of DRAM peak (profiles/)",
+                      "every kernel in it; group_round_kernel (token streaming, 31 % of the step) alone runs at 71 % of DRAM peak (profiles/)",
             "note": "the step is a chain of 9 rounds whose kernels are latency bound at this batch size (serial FNV-1a chain of the "
                     "representatives: 1.5-2.4 us per block; dependent index loads): ~1.75 ms per step whatever the batch size; the "
                     "marginal cost, ~3 ns per prompt, is the DRAM time of the step's measured traffic (%s KB per prompt, ncu); see DESIGN.md"
