@@ -18,9 +18,14 @@
  *     pod -> 12-bit id, device tier -> 4-bit id.  (pod,tier) travels packed in a
  *     kvidx_podtier_t.  The host mirror (kvidx_host.h) owns the string maps;
  *   - all entry points may be called concurrently from many OS threads (cgo
- *     pins one per call).  Calls on one handle are applied in a single total
- *     order (the handle's CUDA stream), which is a valid linearisation of the
- *     reference's mutex-protected index (kvblock/index.go:118);
+ *     pins one per call), as kvblock.Index requires (kvblock/index.go:118).
+ *     The READ path (hash / lookup / score / get_request_key) and the WRITE path
+ *     (add / evict / apply_events) run on separate CUDA streams and overlap on the
+ *     device: a reader sees every slot either before or after an individual
+ *     Add / Evict of that key (table.cuh), which is the guarantee the reference's
+ *     per-key mutex gives.  A write call has taken effect when it returns, so a
+ *     thread reads its own writes (index_test.go:214-278).  Concurrent host-buffer
+ *     kvidx_score_batch* callers are coalesced into one launch;
  *   - there is NO CPU fallback: without a CUDA device kvidx_create fails with
  *     KVIDX_ECUDA.
  */
@@ -34,7 +39,8 @@
 extern "C" {
 #endif
 
-#define KVIDX_ABI_VERSION 1
+#define KVIDX_ABI_VERSION 2   /* 2: read and write path run concurrently; kvidx_apply_events_dev takes the batch sizes;
+                                  kvidx_score_batch_sparse_dev, kvidx_shard_compact; two more stats fields */
 
 /* error codes (negative errno style) */
 #define KVIDX_OK        0
@@ -129,6 +135,8 @@ int kvidx_lookup(kvidx_t* idx, uint32_t model, const uint64_t* keys, int64_t n,
                  const uint64_t* filter, kvidx_podtier_t* podtier_out, uint8_t* cnt_out);
 
 /* Indexer.GetPodScores steps 2-4 fused (indexer.go:141-163) for a batch of prompts.
+ * Callers that arrive while another call's batch is on the device are queued and served together by one launch
+ * (each gets exactly the rows of its own prompts; KVIDX_SUBMIT_QUEUE=0 turns the coalescing off).
  * model: per-prompt model ids, or NULL to use model0 for all.
  * filter: NULL, or n_prompts * ceil(max_pods/64) words (all-zero row == empty set == all pods,
  *         indexer.go:151 / in_memory.go:126).
@@ -185,8 +193,8 @@ int kvidx_apply_events(kvidx_t* idx, const kvidx_event_t* ev, int64_t n_events,
 /* ---- device-resident variants (inputs already in HBM; used by bench `value`, by the
  *      multi-GPU router and by callers that keep token buffers on the device) ------- */
 
-/* Use an external CUDA stream (cudaStream_t as void*) for subsequent calls; NULL restores the
- * handle's own stream. */
+/* Use an external CUDA stream (cudaStream_t as void*) for subsequent READ-path calls; NULL restores the
+ * handle's own stream.  The write path always uses the handle's own write stream. */
 int kvidx_set_stream(kvidx_t* idx, void* cuda_stream);
 int kvidx_synchronize(kvidx_t* idx);
 
@@ -197,12 +205,19 @@ int kvidx_synchronize(kvidx_t* idx);
 int kvidx_score_batch_dev(kvidx_t* idx, const uint32_t* d_tok, const int64_t* d_tok_off, int64_t n_prompts,
                           const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter,
                           double* d_scores_out, uint8_t* d_has_keys_out);
+int kvidx_score_batch_sparse_dev(kvidx_t* idx, const uint32_t* d_tok, const int64_t* d_tok_off, int64_t n_prompts,
+                                 const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter,
+                                 uint16_t* d_pods_out, double* d_scores_out, uint8_t* d_cnt_out, uint8_t* d_has_keys_out);
 int kvidx_hash_keys_dev(kvidx_t* idx, const uint32_t* d_tok, const int64_t* d_tok_off, int64_t n_prompts,
                         const uint64_t* d_parent, const uint8_t* d_parent_valid,
                         const int64_t* d_key_off, uint64_t* d_keys_out);
+/* Pool.digestEvents for a device-resident batch: events stably sorted by pod (queue q owns
+ * d_ev_sorted[d_queue_off[q] .. d_queue_off[q+1])), n_events in all, n_hashes engine hashes behind them.  Asynchronous on
+ * the handle's WRITE stream; read calls issued after it returns are ordered after the batch.  d_n_dropped (may be NULL)
+ * receives the handle's cumulative dropped-event count once the batch is done. */
 int kvidx_apply_events_dev(kvidx_t* idx, const kvidx_event_t* d_ev_sorted, const int64_t* d_queue_off,
-                           int64_t n_queues, const uint64_t* d_hashes, const uint32_t* d_tokens,
-                           int64_t* d_n_dropped);
+                           int64_t n_queues, int64_t n_events, const uint64_t* d_hashes, int64_t n_hashes,
+                           const uint32_t* d_tokens, int64_t* d_n_dropped);
 
 /* ---- hash-range sharding across GPUs (one process per GPU) ------------------------
  * The request and engine tables are partitioned by the top bits of the mixed key.  Every rank maps its peers'
@@ -210,12 +225,19 @@ int kvidx_apply_events_dev(kvidx_t* idx, const kvidx_event_t* d_ev_sorted, const
  * wherever they live: a Score() probe of a remote key is a 64-byte peer load issued from the fused walk, an
  * Add / Evict is a system-scope CAS on the owner's slot.  No collective sits on the data path; NCCL (or any
  * transport) is only needed to exchange the 192-byte handle blobs once.
- * Ingest rule: all events of one pod must be applied through ONE rank (per-pod order, kvevents/pool.go:129-144). */
+ * Ingest rule: all events of one pod must be applied through ONE rank (per-pod order, kvevents/pool.go:129-144).
+ * Before a write batch every owner's fill level is read through the mapped memory; a full owner fails the call with
+ * KVIDX_ENOSPC (and an insert that still finds no slot is refused and counted), nothing spins. */
 #define KVIDX_SHARD_HANDLE_BYTES 192
 int kvidx_shard_export(kvidx_t* idx, void* handle_out /* KVIDX_SHARD_HANDLE_BYTES */);
 int kvidx_shard_import(kvidx_t* idx, uint32_t rank, const void* handle /* from that rank's kvidx_shard_export */);
 /* same-process variant (several GPUs driven by one process, e.g. tests): map `other`'s shard directly */
 int kvidx_shard_attach(kvidx_t* idx, uint32_t rank, kvidx_t* other);
+/* Drop the tombstones of THIS rank's shard (steady BlockStored / BlockRemoved churn leaves them behind; a write call
+ * answers KVIDX_ENOSPC when an owner runs out of room).  Collective by contract: every rank calls it between two barriers
+ * of the embedding program, no rank touches the index meanwhile (kvidx.dist.compact_shards does exactly that).  On an
+ * unsharded handle it is the compaction the write path runs by itself when needed. */
+int kvidx_shard_compact(kvidx_t* idx);
 
 /* ---- introspection ------------------------------------------------------------ */
 typedef struct kvidx_stats {
@@ -227,6 +249,9 @@ typedef struct kvidx_stats {
     uint64_t engine_slots;
     uint64_t rebuilds;
     uint64_t kernel_launches;   /* kernels this handle has launched so far      */
+    uint64_t rehashed_events;   /* BlockStored events whose parent resolved differently at apply time than when their
+                                   keys were precomputed (kernels_write.cuh phase 1): re-hashed in place             */
+    uint64_t coalesced_calls;   /* host-buffer Score() calls that were served as part of another call's launch      */
 } kvidx_stats_t;
 int kvidx_get_stats(kvidx_t* idx, kvidx_stats_t* out);
 

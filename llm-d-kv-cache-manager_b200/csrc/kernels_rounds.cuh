@@ -119,15 +119,29 @@ __device__ __forceinline__ void chunk_load(const uint32_t* sp, int nw, int lane,
 }
 
 constexpr int kGroupRing = 4;            // chunk slots per warp: one being examined, two in flight, the anchor (deeper rings measured: slower)
-struct GroupSmem { uint4 ring[kGroupThreads / 32][kGroupRing][4][32]; };     // 64 KB
+struct GroupSmem {
+    uint4 ring[kGroupThreads / 32][kGroupRing][4][32];                       // 64 KB
+    unsigned long long bar[kGroupThreads / 32][kGroupRing];                  // TMA variant: one mbarrier per rotating slot
+};
 
-template <int BS>
+// TMA = true: a chunk (<= 2 KB, contiguous, 16-byte aligned) is ONE cp.async.bulk issued by an elected lane onto the slot's
+// mbarrier (UBLKCP in SASS) instead of four 16-byte cp.async per lane (LDGSTS); chunks that do not start on a 16-byte
+// boundary are copied with plain loads in both variants.
+template <int BS, bool TMA>
 __global__ void __launch_bounds__(kGroupThreads, 3)
 group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int dedup) {
     static_assert(BS == 16 && kRoundBlocks == 32, "a chunk is 4 x 32 lanes x 16 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw_g[];
     uint4 (*ring)[4][32] = reinterpret_cast<GroupSmem*>(smem_raw_g)->ring[threadIdx.x >> 5];
+    unsigned long long* bar = reinterpret_cast<GroupSmem*>(smem_raw_g)->bar[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
+    uint32_t tma_pending = 0, tma_phase = 0;          // per rotating slot: a bulk copy is in flight / parity of its next wait
+    if (TMA) {
+        if (lane == 0) for (int s = 0; s < kGroupRing - 1; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+        __syncwarp();
+    }
     const unsigned int n_act = rb.n_act[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) { rb.n_act[cur ^ 1] = 0; rb.n_hl[0] = 0; rb.n_hl[1] = 0; rb.n_hl[2] = 0; rb.n_hl[3] = 0; }   // lists built below / by G2
     const unsigned int total_warps = gridDim.x * (kGroupThreads / 32);
@@ -172,17 +186,23 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 const uint32_t* sp = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)tp, qi));
                 const int nw = __shfl_sync(0xffffffffu, nb, qi) * BS;
                 const bool al = (reinterpret_cast<uintptr_t>(sp) & 15u) == 0;
+                if (TMA && al) {
+                    __syncwarp();                              // every lane has taken the slot's previous chunk into registers
+                    if (lane == 0) { fence_proxy_async(); mbar_expect_tx(&bar[slot], (uint32_t)nw * 4u); tma_load_1d(&ring[slot][0][0], sp, (uint32_t)nw * 4u, &bar[slot]); }
+                    tma_pending |= 1u << slot;
+                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int w0 = (c * 32 + lane) * 4;
                     uint4* dst = &ring[slot][c][lane];
                     if (w0 < nw) {
-                        if (al) cp_async_16(smem_addr(dst), sp + w0);
+                        if (TMA && al) {}
+                        else if (al) cp_async_16(smem_addr(dst), sp + w0);
                         else *dst = make_uint4(__ldg(sp + w0), __ldg(sp + w0 + 1), __ldg(sp + w0 + 2), __ldg(sp + w0 + 3));
                     } else *dst = make_uint4(0, 0, 0, 0);
                 }
             }
-            cp_async_commit();
+            if (!TMA) cp_async_commit();
         };
         constexpr int RS = kGroupRing - 1;            // rotating slots; slot RS holds the anchor
         constexpr int PD = RS - 1;                    // chunks in flight
@@ -203,7 +223,11 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 pend &= pend - 1;
                 issue(issued % RS, qi); ++issued;
             }
-            cp_async_wait<PD>();
+            if (TMA) {
+                const int s_ = ord % RS;
+                if ((tma_pending >> s_) & 1u) { mbar_wait(&bar[s_], (tma_phase >> s_) & 1u); tma_phase ^= 1u << s_; tma_pending &= ~(1u << s_); }
+                __syncwarp();                                  // plain-store chunks (unaligned starts, zero tails) are visible too
+            } else cp_async_wait<PD>();
             uint4 v[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) v[c] = ring[ord % RS][c][lane];
@@ -261,7 +285,7 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             }
             ++ord;
         }
-        cp_async_wait<0>();
+        if (!TMA) cp_async_wait<0>();
         // election among the prompts that are not members of an anchor's class
         uint32_t cand = kRoleSelf;
         if (cls && !eqanch) {
@@ -967,7 +991,8 @@ __global__ void count_distinct_prefixes_kernel(const uint64_t* __restrict__ fp_s
 
 inline int rounds_init() {
     if (cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
-    if (cudaFuncSetAttribute(group_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(group_round_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(group_round_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GroupSmem)) != cudaSuccess) return -1;
     return 0;
 }
 

@@ -7,8 +7,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/kvidx.h"
@@ -17,6 +22,7 @@
 #include "kernels_score.cuh"
 #include "kernels_rounds.cuh"
 #include "kernels_rounds_plain.cuh"
+#include "kernels_coop.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace kvx;
@@ -80,24 +86,62 @@ bool is_device_accessible_host(const void* p) {
 
 }  // namespace
 
+// Concurrent host-buffer Score() callers (one goroutine / OS thread per RPC, server.go:70-96) are coalesced: whoever finds
+// no batch in progress becomes the leader, takes everything that has queued up meanwhile, runs it as ONE batch through the
+// pipeline and wakes the owners.  No dedicated thread, no artificial delay: a lone caller goes straight through with its
+// own buffers; under load the batch size grows by itself to what arrived during the previous launch.
+struct SubmitReq {
+    const uint32_t* tok; const int64_t* tok_off; int64_t n; const uint32_t* model; uint32_t model0; const uint64_t* filter;
+    double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* sp_cnt; uint8_t* has_keys;
+    int rc = 0; bool done = false, promote = false; std::string err;
+};
+struct SubmitQueue {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<SubmitReq*> pending;
+    bool leader_active = false;
+    bool enabled = true;
+    int64_t max_prompts = 65536, max_tokens = 64ll << 20;
+    std::atomic<uint64_t> coalesced{0}, batches{0};
+    // combined host-side batch (pinned), owned by the current leader
+    void* h_in = nullptr; size_t h_in_cap = 0;
+    void* h_out = nullptr; size_t h_out_cap = 0;
+};
+
 struct kvidx {
     kvidx_config_t cfg{};
     TableView tv{};
     int device = 0;
     int sm_count = 148;
-    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+    // Read path (Score / Lookup / hash) and write path (Add / Evict / events) run on their own streams and behind their own
+    // mutexes: a Score() call and an event batch overlap on the device (table.cuh: readers never wait for writers).
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, own_wstream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr};
+    cudaEvent_t ev_write = nullptr;   // last asynchronous (device-resident) write batch: later reads are ordered after it
     Counters* d_cnt = nullptr;
-    Counters* h_cnt = nullptr;     // pinned mirror
-    uint64_t rebuilds = 0, launches = 0;
+    Counters* h_cnt = nullptr;     // pinned mirror (write side)
+    Counters* d_cnt_all = nullptr; // sharded: every owner's counters, gathered before a write batch
+    Counters* h_cnt_all = nullptr;
+    uint64_t rebuilds = 0;
+    std::atomic<uint64_t> launches{0};
     int64_t last_batch_events = 1 << 20;   // events in the batch being applied (sizes the stamp range)
-    unsigned long long clock = 1;   // exact-LRU mode: recency stamps handed to kernels (calls on a handle are serialised)
-    std::mutex mu;
-    // scratch (guarded by mu)
-    DevBuf d_tok[2], d_off[2], d_model[2], d_filter[2], d_out[2], d_aux[2], d_misc, d_ev, d_hash, d_evtok, d_qoff;
-    PinBuf h_stage[2], h_out[2], h_misc;
+    std::atomic<unsigned long long> clock{1};   // exact-LRU mode: recency stamps handed to kernels
+    std::mutex mu_r, mu_w;          // read-side / write-side scratch and stream
+    std::shared_mutex tables;       // shared: any call that launches on the tables; exclusive: rebuild swaps them
+    // read-side scratch (guarded by mu_r)
+    DevBuf d_tok[2], d_off[2], d_model[2], d_filter[2], d_out[2], d_aux[2], d_rmisc;
+    PinBuf h_stage[2], h_out[2];
+    // write-side scratch (guarded by mu_w)
+    DevBuf d_misc, d_ev, d_hash, d_evtok, d_qoff, d_wkeys, d_wpred, d_wready, d_wmap;
+    PinBuf h_misc;
+    int write_phase1 = -1;          // -1: by batch size, 0: never, 1: always (phase 1 = hash_events_kernel)
+    int64_t write_phase1_min = 1024; // engine hashes in a batch from which phase 1 pays
     int score_kernel = 2;          // 1 = v1 (thread per prompt, global tokens), 2 = tuned
-    int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 = always the round pipeline
+    int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 / 3 = always the plain / class round pipeline,
+                                   // 4 = always the warp-per-prompt cooperative kernel
+    int64_t coop_max = 2048;       // batches up to this many prompts use the warp-per-prompt cooperative kernel
+    int group_tma = 1;             // class pipeline: token chunks by TMA bulk copy (0: cp.async)
+    struct SubmitQueue* queue = nullptr;   // coalesces concurrent host-buffer Score() callers (submit.cuh)
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
     int64_t classes_min = 393216;  // ... and at least this large, the prefix-class round pipeline
     double classes_min_sharing = 0.85;   // ... if at least this fraction of the batch follows a representative in round 0
@@ -122,55 +166,107 @@ int check_shards(kvidx* x) {
     return 0;
 }
 
-unsigned long long reserve_stamps(kvidx* x, unsigned long long n) { const unsigned long long b = x->clock; x->clock += n + 1; return b; }
+unsigned long long reserve_stamps(kvidx* x, unsigned long long n) { return x->clock.fetch_add(n + 1); }
+
+// The stream write kernels go to.  Exact-LRU mode keeps reads and writes on ONE stream (reads write recency stamps, so the
+// two sides are not independent there); otherwise the write path has its own.
+cudaStream_t wstream(kvidx* x) { return x->tv.req_stamp ? x->stream : x->own_wstream; }
+
+// Locks of a call.  Read-side calls take mu_r (+ mu_w in exact-LRU mode, where everything is serialised as in round 1),
+// write-side calls mu_w; both hold `tables` shared while they launch.  Only rebuild() takes `tables` exclusively.
+struct ReadGuard {
+    std::unique_lock<std::mutex> w, r;
+    std::shared_lock<std::shared_mutex> t;
+    explicit ReadGuard(kvidx* x) {
+        if (x->tv.req_stamp) w = std::unique_lock<std::mutex>(x->mu_w);
+        r = std::unique_lock<std::mutex>(x->mu_r);
+        t = std::shared_lock<std::shared_mutex>(x->tables);
+    }
+};
 
 int refresh_counters(kvidx* x) {
-    CK(cudaMemcpyAsync(x->h_cnt, x->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
+    CK(cudaMemcpyAsync(x->h_cnt, x->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, wstream(x)));
+    CK(cudaStreamSynchronize(wstream(x)));
     return 0;
 }
 
-int alloc_tables(kvidx* x, uint64_t req_slots, uint64_t eng_slots, ReqSlot** req, EngSlot** eng) {
+int alloc_tables(kvidx* x, uint64_t req_slots, uint64_t eng_slots, ReqSlot** req, EngSlot** eng, cudaStream_t st) {
+    *req = nullptr; *eng = nullptr;
     CK(cudaMalloc((void**)req, req_slots * sizeof(ReqSlot)));
-    CK(cudaMalloc((void**)eng, eng_slots * sizeof(EngSlot)));
-    CK(cudaMemsetAsync(*req, 0, req_slots * sizeof(ReqSlot), x->stream));
-    CK(cudaMemsetAsync(*eng, 0, eng_slots * sizeof(EngSlot), x->stream));
+    cudaError_t e = cudaMalloc((void**)eng, eng_slots * sizeof(EngSlot));
+    if (e != cudaSuccess) { cudaFree(*req); *req = nullptr; return fail(KVIDX_ENOMEM, "cudaMalloc of %llu engine slots: %s", (unsigned long long)eng_slots, cudaGetErrorString(e)); }
+    CK(cudaMemsetAsync(*req, 0, req_slots * sizeof(ReqSlot), st));
+    CK(cudaMemsetAsync(*eng, 0, eng_slots * sizeof(EngSlot), st));
     return 0;
 }
 
-// Drop tombstones by re-inserting live slots into fresh tables.
-int rebuild(kvidx* x) {
-    if (x->tv.shard_bits) return fail(KVIDX_ENOSPC, "sharded table needs compaction (tombstones); not supported while peers map this shard");
+// Drop tombstones: re-insert the live slots into fresh tables.  Caller holds mu_w and `tables` EXCLUSIVELY; every stream of
+// the device is drained first (asynchronous Score() calls may still be reading the old tables).
+//   unsharded: the fresh tables replace the old ones;
+//   sharded  : peers have this shard mapped (CUDA IPC), so the fresh tables are copied back into the same allocation.  The
+//              caller of kvidx_shard_compact guarantees that no rank touches the index meanwhile (a barrier either side).
+int rebuild(kvidx* x, bool in_place) {
+    CK(cudaDeviceSynchronize());
+    cudaStream_t st = wstream(x);
     const uint64_t rs = x->tv.req_mask + 1, es = x->tv.eng_mask + 1;
     ReqSlot* nreq; EngSlot* neng;
-    int rc = alloc_tables(x, rs, es, &nreq, &neng);
+    int rc = alloc_tables(x, rs, es, &nreq, &neng, st);
     if (rc) return rc;
     const int T = 256;
     unsigned long long* nstamp = nullptr;
-    if (x->tv.req_stamp) { CK(cudaMalloc((void**)&nstamp, rs * 8)); CK(cudaMemsetAsync(nstamp, 0, rs * 8, x->stream)); }
-    rebuild_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, rs, nreq, rs - 1, x->tv.req_stamp, nstamp);
-    rebuild_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, x->stream>>>(x->tv.eng, es, neng, es - 1);
+    if (x->tv.req_stamp) { CK(cudaMalloc((void**)&nstamp, rs * 8)); CK(cudaMemsetAsync(nstamp, 0, rs * 8, st)); }
+    rebuild_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, st>>>(x->tv.req, rs, nreq, rs - 1, x->tv.req_stamp, nstamp);
+    rebuild_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, st>>>(x->tv.eng, es, neng, es - 1);
     x->launches += 2;
     CK(cudaGetLastError());
     // zero the tombstone counters on the device
-    CK(cudaMemsetAsync(&x->d_cnt->req_tomb, 0, sizeof(unsigned long long), x->stream));
-    CK(cudaMemsetAsync(&x->d_cnt->eng_tomb, 0, sizeof(unsigned long long), x->stream));
-    CK(cudaStreamSynchronize(x->stream));
-    cudaFree(x->tv.req); cudaFree(x->tv.eng);
-    if (x->tv.req_stamp) { cudaFree(x->tv.req_stamp); x->tv.req_stamp = nstamp; }
-    x->tv.req = nreq; x->tv.eng = neng;
-    x->tv.req_peer[0] = nreq; x->tv.eng_peer[0] = neng;
+    CK(cudaMemsetAsync(&x->d_cnt->req_tomb, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(&x->d_cnt->eng_tomb, 0, sizeof(unsigned long long), st));
+    if (in_place) {
+        CK(cudaMemcpyAsync(x->tv.req, nreq, rs * sizeof(ReqSlot), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(x->tv.eng, neng, es * sizeof(EngSlot), cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        cudaFree(nreq); cudaFree(neng);
+    } else {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(x->tv.req); cudaFree(x->tv.eng);
+        if (x->tv.req_stamp) { cudaFree(x->tv.req_stamp); x->tv.req_stamp = nstamp; }
+        x->tv.req = nreq; x->tv.eng = neng;
+        x->tv.req_peer[0] = nreq; x->tv.eng_peer[0] = neng;
+    }
     ++x->rebuilds;
     return refresh_counters(x);
 }
 
-// Make room for up to `incoming` new keys in each table before a write batch.
+// Make room for up to `incoming` new keys in each table before a write batch.  Caller holds mu_w and NOT `tables`.
+//   unsharded: this handle's counters decide; tombstones are compacted away here when they are what fills the table;
+//   sharded  : the keys may land on any owner, so every owner's counters are read (through the mapped peer memory) and
+//              each must have room for the whole batch; compaction is the collective kvidx_shard_compact.
 int ensure_room(kvidx* x, uint64_t incoming) {
     const uint64_t rs = x->tv.req_mask + 1, es = x->tv.eng_mask + 1;
     auto over = [&](uint64_t full, uint64_t tomb, uint64_t slots) { return (full + tomb + incoming) * 10 > slots * 8; };
+    if (x->tv.shard_bits) {
+        const uint32_t ns = 1u << x->tv.shard_bits;
+        gather_counters_kernel<<<1, 32, 0, wstream(x)>>>(x->tv, x->d_cnt_all);
+        x->launches += 1;
+        CK(cudaMemcpyAsync(x->h_cnt_all, x->d_cnt_all, sizeof(Counters) * ns, cudaMemcpyDeviceToHost, wstream(x)));
+        CK(cudaStreamSynchronize(wstream(x)));
+        for (uint32_t r = 0; r < ns; ++r) {
+            const Counters& c = x->h_cnt_all[r];
+            if ((c.req_full + c.req_tomb + incoming) * 10 > rs * 9 || (c.eng_full + c.eng_tomb + incoming) * 10 > es * 9)
+                return fail(KVIDX_ENOSPC, "shard %u full: %llu keys + %llu tombstones + %llu incoming in %llu slots%s", r,
+                            (unsigned long long)c.req_full, (unsigned long long)c.req_tomb, (unsigned long long)incoming, (unsigned long long)rs,
+                            (c.req_tomb || c.eng_tomb) ? " (kvidx_shard_compact on every rank drops the tombstones)" : "");
+        }
+        return 0;
+    }
     const Counters& c = *x->h_cnt;
     if (over(c.req_full, c.req_tomb, rs) || over(c.eng_full, c.eng_tomb, es)) {
-        if (c.req_tomb || c.eng_tomb) { int rc = rebuild(x); if (rc) return rc; }
+        if (c.req_tomb || c.eng_tomb) {
+            std::unique_lock<std::shared_mutex> tl(x->tables);
+            int rc = rebuild(x, false);
+            if (rc) return rc;
+        }
         const Counters& d = *x->h_cnt;
         if ((d.req_full + incoming) * 10 > rs * 9 || (d.eng_full + incoming) * 10 > es * 9)
             return fail(KVIDX_ENOSPC, "table full: %llu request keys + %llu incoming in %llu slots",
@@ -189,18 +285,19 @@ int enforce_caps(kvidx* x) {
     unsigned long long* d_v = x->d_misc.as<unsigned long long>();
     const uint64_t rs = x->tv.req_mask + 1, es = x->tv.eng_mask + 1;
     const int T = 256;
+    cudaStream_t st = wstream(x);
     while (x->h_cnt->req_full > x->tv.capacity) {
-        CK(cudaMemsetAsync(d_v, 0xff, 8, x->stream));
-        lru_min_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, x->tv.req_stamp, rs, d_v);
-        lru_drop_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, x->stream>>>(x->tv.req, x->tv.req_stamp, rs, d_v, x->d_cnt);
+        CK(cudaMemsetAsync(d_v, 0xff, 8, st));
+        lru_min_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, st>>>(x->tv.req, x->tv.req_stamp, rs, d_v);
+        lru_drop_req_kernel<<<(unsigned)((rs + T - 1) / T), T, 0, st>>>(x->tv.req, x->tv.req_stamp, rs, d_v, x->d_cnt);
         x->launches += 2;
         CK(cudaGetLastError());
         if ((rc = refresh_counters(x))) return rc;
     }
     while (x->h_cnt->eng_full > x->tv.capacity) {
-        CK(cudaMemsetAsync(d_v, 0xff, 8, x->stream));
-        lru_min_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, x->stream>>>(x->tv.eng, es, d_v);
-        lru_drop_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, x->stream>>>(x->tv.eng, es, d_v, x->d_cnt);
+        CK(cudaMemsetAsync(d_v, 0xff, 8, st));
+        lru_min_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, st>>>(x->tv.eng, es, d_v);
+        lru_drop_eng_kernel<<<(unsigned)((es + T - 1) / T), T, 0, st>>>(x->tv.eng, es, d_v, x->d_cnt);
         x->launches += 2;
         CK(cudaGetLastError());
         if ((rc = refresh_counters(x))) return rc;
@@ -322,7 +419,8 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
             const int64_t m = psz[q];
             if (m <= 0) continue;
             const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads - 1) / kGroupThreads, (int64_t)x->sm_count * (np == 1 ? 3 : x->rounds_grid[0]));
-            group_round_kernel<16><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
+            if (x->group_tma) group_round_kernel<16, true><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
+            else group_round_kernel<16, false><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
             const unsigned lgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : x->rounds_grid[1]));
             group_lists_kernel<16><<<lgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2);
         }
@@ -432,14 +530,22 @@ int launch_score(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t 
         score_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
                                                                   o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, sb, stride);
         x->launches += 1;
-    } else if (x->tv.block_size == 16 && n < (1ll << 31) && (x->score_path >= 2 || (x->score_path == 0 && n >= x->rounds_min))) {
+    } else if (x->tv.block_size == 16 && (x->score_path == 4 || (x->score_path == 0 && n <= x->coop_max))) {
+        // small batches: a warp per prompt, warp-cooperative hashing, TMA-staged tokens (kernels_coop.cuh)
+        ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
+        const int64_t ctas = std::min<int64_t>((n + kCoopWarps - 1) / kCoopWarps, (int64_t)x->sm_count * 4);
+        coop_score_kernel<16><<<(unsigned)ctas, kCoopThreads, sizeof(CoopSmem), st>>>(x->tv, a);
+        x->launches += 1;
+    } else if (x->tv.block_size == 16 && n < (1ll << 31) && ((x->score_path >= 2 && x->score_path <= 3) || (x->score_path == 0 && n >= x->rounds_min))) {
         // path 2: plain rounds, 3: prefix classes; automatic: by batch size (the class pipeline has a fixed cost per round)
         const bool classes = x->score_path == 3 || (x->score_path == 0 && n >= x->classes_min);
         return classes ? launch_score_rounds(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks)
                        : launch_score_rounds_plain(x, d_tok, d_off, tok_base, n, d_model, model0, d_filter, o, st, max_blocks);
     } else {
+        uint64_t nl = 0;
         int rc = launch_score_tuned(x->tv, x->sm_count, d_tok, d_off, tok_base, n, d_model, model0, d_filter,
-                                    o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, &x->d_cnt->pad, st, &x->launches);
+                                    o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, &x->d_cnt->pad, st, &nl);
+        x->launches += nl;
         if (rc) return fail(KVIDX_ECUDA, "score launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     CK(cudaGetLastError());
@@ -457,6 +563,9 @@ int check_csr(const int64_t* off, int64_t n) {
 //   x->stream   : score kernel                      (waits ev_h2d, records ev_k[slot])
 //   d2h_stream  : results -> pinned host            (waits ev_k, records ev_done[slot])
 // Caller buffers that are already pinned are used directly (no staging memcpy).
+int score_host_locked(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
+                      const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys);
+
 int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
                const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys) {
     if (n < 0 || !tok_off) return fail(KVIDX_EINVAL, "bad arguments");
@@ -464,8 +573,23 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
     int rc = check_csr(tok_off, n);
     if (rc) return rc;
     if (tok_off[n] > tok_off[0] && !tok) return fail(KVIDX_EINVAL, "NULL tokens");
-    std::lock_guard<std::mutex> g(x->mu);
+    ReadGuard g(x);
     CK(cudaSetDevice(x->device));
+    rc = score_host_locked(x, tok, tok_off, n, model, model0, filter, dense, sp_pods, sp_scores, sp_cnt, has_keys);
+    if (rc) {
+        // an error in the middle of the pipeline: copies may still be reading the caller's buffers and this handle's staging
+        // slots -- drain the three streams before the caller gets its buffers back (the error text is kept)
+        const std::string keep = g_err;
+        cudaStreamSynchronize(x->copy_stream); cudaStreamSynchronize(x->stream); cudaStreamSynchronize(x->d2h_stream);
+        cudaGetLastError();
+        g_err = keep;
+    }
+    return rc;
+}
+
+int score_host_locked(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
+                      const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys) {
+    int rc = 0;
     const uint32_t P = x->tv.max_pods, FW = x->tv.filter_words;
     const bool sparse = sp_cnt != nullptr;
     const size_t out_row = sparse ? (size_t)kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 2 : (size_t)P * sizeof(double) + 1;
@@ -496,7 +620,8 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
         }
         return 0;
     };
-    // the first chunk must see everything already queued on the handle's stream (earlier writes)
+    // the first chunk must see everything already queued on the handle's stream, and asynchronous write batches issued before
+    CK(cudaStreamWaitEvent(s_k, x->ev_write, 0));
     CK(cudaEventRecord(x->ev_k[0], s_k));
     CK(cudaStreamWaitEvent(s_in, x->ev_k[0], 0));
     int64_t i0 = 0;
@@ -578,6 +703,158 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
     return 0;
 }
 
+
+int pin_need(void** p, size_t* cap, size_t n) {
+    if (n <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = n + n / 4 + 4096;
+    CK(cudaMallocHost(p, want));
+    *cap = want;
+    return 0;
+}
+
+// Several callers' requests as one batch: tokens are gathered into one pinned buffer (CSR rebuilt), per-prompt model ids and
+// filter rows materialised if any request carries them, one pass through score_host, results scattered to the owners.
+int run_combined(kvidx* x, SubmitQueue* q, const std::vector<SubmitReq*>& batch) {
+    const uint32_t P = x->tv.max_pods, FW = x->tv.filter_words;
+    int64_t n = 0, nt = 0;
+    bool any_model = false, any_filter = false, want_has = false;
+    for (const SubmitReq* r : batch) {
+        n += r->n; nt += r->tok_off[r->n] - r->tok_off[0];
+        any_model |= r->model != nullptr || r->model0 != batch[0]->model0; any_filter |= r->filter != nullptr; want_has |= r->has_keys != nullptr;
+    }
+    const bool sparse = batch[0]->sp_cnt != nullptr;
+    const size_t in_bytes = (size_t)nt * 4 + 64 + (size_t)(n + 1) * 8 + (any_model ? (size_t)n * 4 : 0) + 64 + (any_filter ? (size_t)n * FW * 8 : 0);
+    const size_t out_bytes = sparse ? (size_t)n * (kMaxEnt * 10 + 2) + 64 : (size_t)n * (P * 8 + 1) + 64;
+    int rc = pin_need(&q->h_in, &q->h_in_cap, in_bytes); if (rc) return rc;
+    rc = pin_need(&q->h_out, &q->h_out_cap, out_bytes); if (rc) return rc;
+    uint8_t* hi = static_cast<uint8_t*>(q->h_in);
+    uint32_t* tok = reinterpret_cast<uint32_t*>(hi); size_t o = ((size_t)nt * 4 + 63) & ~(size_t)63;
+    int64_t* off = reinterpret_cast<int64_t*>(hi + o); o += (size_t)(n + 1) * 8;
+    uint32_t* model = nullptr; uint64_t* filter = nullptr;
+    if (any_model) { model = reinterpret_cast<uint32_t*>(hi + o); o += ((size_t)n * 4 + 63) & ~(size_t)63; }
+    if (any_filter) { filter = reinterpret_cast<uint64_t*>(hi + o); }
+    int64_t at = 0, tat = 0;
+    off[0] = 0;
+    for (const SubmitReq* r : batch) {
+        const int64_t tb = r->tok_off[0], rt = r->tok_off[r->n] - tb;
+        if (rt > 0) memcpy(tok + tat, r->tok + tb, (size_t)rt * 4);
+        for (int64_t i = 0; i < r->n; ++i) off[at + i + 1] = tat + (r->tok_off[i + 1] - tb);
+        if (model) for (int64_t i = 0; i < r->n; ++i) model[at + i] = r->model ? r->model[i] : r->model0;
+        if (filter) { if (r->filter) memcpy(filter + (size_t)at * FW, r->filter, (size_t)r->n * FW * 8); else memset(filter + (size_t)at * FW, 0, (size_t)r->n * FW * 8); }
+        at += r->n; tat += rt;
+    }
+    uint8_t* ho = static_cast<uint8_t*>(q->h_out);
+    if (!sparse) {
+        double* dense = reinterpret_cast<double*>(ho); uint8_t* has = ho + (size_t)n * P * 8;
+        rc = score_host(x, tok, off, n, model, batch[0]->model0, filter, dense, nullptr, nullptr, nullptr, has);
+        if (rc) return rc;
+        at = 0;
+        for (SubmitReq* r : batch) {
+            memcpy(r->dense, dense + (size_t)at * P, (size_t)r->n * P * 8);
+            if (r->has_keys) memcpy(r->has_keys, has + at, (size_t)r->n);
+            at += r->n;
+        }
+    } else {
+        double* sc = reinterpret_cast<double*>(ho); uint16_t* pods = reinterpret_cast<uint16_t*>(ho + (size_t)n * kMaxEnt * 8);
+        uint8_t* cnt = ho + (size_t)n * kMaxEnt * 10; uint8_t* has = cnt + n;
+        rc = score_host(x, tok, off, n, model, batch[0]->model0, filter, nullptr, pods, sc, cnt, has);
+        if (rc) return rc;
+        at = 0;
+        for (SubmitReq* r : batch) {
+            memcpy(r->sp_scores, sc + (size_t)at * kMaxEnt, (size_t)r->n * kMaxEnt * 8);
+            memcpy(r->sp_pods, pods + (size_t)at * kMaxEnt, (size_t)r->n * kMaxEnt * 2);
+            memcpy(r->sp_cnt, cnt + at, (size_t)r->n);
+            if (r->has_keys) memcpy(r->has_keys, has + at, (size_t)r->n);
+            at += r->n;
+        }
+    }
+    (void)want_has;
+    return 0;
+}
+
+int submit_score(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
+                 const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys) {
+    SubmitQueue* q = x->queue;
+    // big batches and malformed calls go straight through (score_host validates); so does everything when the queue is off
+    if (!q || !q->enabled || n <= 0 || !tok_off || n > q->max_prompts / 4)
+        return score_host(x, tok, tok_off, n, model, model0, filter, dense, sp_pods, sp_scores, sp_cnt, has_keys);
+    if (int rc = check_csr(tok_off, n)) return rc;
+    if (tok_off[n] > tok_off[0] && !tok) return fail(KVIDX_EINVAL, "NULL tokens");
+    SubmitReq me{tok, tok_off, n, model, model0, filter, dense, sp_pods, sp_scores, sp_cnt, has_keys};
+    {
+        std::unique_lock<std::mutex> lk(q->mu);
+        q->pending.push_back(&me);
+        if (q->leader_active) {
+            q->cv.wait(lk, [&] { return me.done || me.promote; });
+            if (me.done) { if (me.rc) g_err = me.err; return me.rc; }
+            // promoted: the previous leader left with work still queued (this request among it)
+        } else q->leader_active = true;
+    }
+    for (;;) {
+        std::vector<SubmitReq*> batch;
+        {
+            std::unique_lock<std::mutex> lk(q->mu);
+            if (me.done) {                                    // my own request is served: hand the queue to the next owner
+                if (q->pending.empty()) q->leader_active = false;
+                else { q->pending.front()->promote = true; }
+                lk.unlock();
+                q->cv.notify_all();
+                if (me.rc) g_err = me.err;
+                return me.rc;
+            }
+            const bool sparse = q->pending.front()->sp_cnt != nullptr;
+            int64_t np = 0, ntok = 0;
+            for (auto it = q->pending.begin(); it != q->pending.end();) {
+                SubmitReq* r = *it;
+                const int64_t rt = r->tok_off[r->n] - r->tok_off[0];
+                if ((r->sp_cnt != nullptr) != sparse) { ++it; continue; }
+                if (!batch.empty() && (np + r->n > q->max_prompts || ntok + rt > q->max_tokens)) break;
+                batch.push_back(r); np += r->n; ntok += rt;
+                it = q->pending.erase(it);
+            }
+        }
+        int rc;
+        if (batch.size() == 1) {
+            SubmitReq* r = batch[0];
+            rc = score_host(x, r->tok, r->tok_off, r->n, r->model, r->model0, r->filter, r->dense, r->sp_pods, r->sp_scores, r->sp_cnt, r->has_keys);
+        } else {
+            rc = run_combined(x, q, batch);
+            q->coalesced += batch.size();
+        }
+        q->batches += 1;
+        {
+            std::lock_guard<std::mutex> lk(q->mu);
+            for (SubmitReq* r : batch) { r->rc = rc; if (rc) r->err = g_err; r->done = true; }
+        }
+        q->cv.notify_all();
+    }
+}
+
+SubmitQueue* new_submit_queue() {
+    SubmitQueue* q = new SubmitQueue();
+    if (const char* k = getenv("KVIDX_SUBMIT_QUEUE")) q->enabled = atoi(k) != 0;
+    return q;
+}
+void delete_submit_queue(SubmitQueue* q) {
+    if (!q) return;
+    if (q->h_in) cudaFreeHost(q->h_in);
+    if (q->h_out) cudaFreeHost(q->h_out);
+    delete q;
+}
+uint64_t submit_queue_coalesced(SubmitQueue* q) { return q->coalesced.load(); }
+
+// TokensToKVBlockKeys for a CSR batch on the device (token_processor.go:141-162)
+int launch_hash_keys(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n, const uint64_t* d_parent,
+                     const uint8_t* d_pv, const int64_t* d_koff, uint64_t* d_keys, cudaStream_t st) {
+    const int T = 128;
+    hash_keys_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, d_tok, d_off, tok_base, n, d_parent, d_pv, d_koff, 0, d_keys);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -624,6 +901,86 @@ uint32_t kvidx_queue_index(const char* pod, size_t n, uint32_t concurrency) {
 void* kvidx_host_alloc(size_t bytes) { void* p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void kvidx_host_free(void* p) { if (p) cudaFreeHost(p); }
 
+namespace {
+int create_impl(const kvidx_config_t& c, kvidx* x) {
+    CK(cudaSetDevice(c.device));
+    x->cfg = c;
+    x->device = c.device;
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    x->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return fail(KVIDX_ECUDA, "device sm_%d%d is not Blackwell; libkvidx is built for sm_100a only", prop.major, prop.minor);
+    CK(cudaStreamCreateWithFlags(&x->own_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&x->own_wstream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking));
+    for (int q = 0; q < kMaxParts - 1; ++q) {
+        CK(cudaStreamCreateWithFlags(&x->aux_stream[q], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&x->ev_join[q], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&x->ev_write, cudaEventDisableTiming));
+    x->stream = x->own_stream;
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&x->ev_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&x->ev_k[i], cudaEventDisableTiming));
+    }
+    uint32_t shard_bits = 0;
+    if (c.shard_count > 1) {
+        if (c.shard_count > 8 || (c.shard_count & (c.shard_count - 1)) || c.shard_rank >= c.shard_count) return fail(KVIDX_EINVAL, "shard_count must be a power of two <= 8 and shard_rank < shard_count");
+        while ((1u << shard_bits) < c.shard_count) ++shard_bits;
+    }
+    const uint64_t per_shard = c.shard_count > 1 ? (c.capacity + c.shard_count - 1) / c.shard_count : c.capacity;
+    uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(4 * per_shard, 1024));
+    if (slots < 1024) slots = 1024;
+    TableView& t = x->tv;
+    t.req_mask = slots - 1; t.eng_mask = slots - 1;
+    t.capacity = c.capacity; t.init_hash = c.init_hash; t.block_size = c.block_size; t.pods_per_key = c.pods_per_key;
+    t.max_pods = c.max_pods; t.filter_words = (c.max_pods + 63) / 64;
+    for (int i = 0; i < 16; ++i) t.weight[i] = (uint32_t)i < c.n_tier_weights ? c.tier_weight[i] : 1.0;
+    t.req_stamp = nullptr;
+    int rc = alloc_tables(x, slots, slots, &t.req, &t.eng, x->stream);
+    if (rc) return rc;
+    if (c.lru_exact) {
+        if (c.shard_count > 1) return fail(KVIDX_EINVAL, "lru_exact is not supported on a sharded index");
+        CK(cudaMalloc((void**)&t.req_stamp, slots * 8));
+        CK(cudaMemsetAsync(t.req_stamp, 0, slots * 8, x->stream));
+    }
+    CK(cudaMalloc((void**)&x->d_cnt, sizeof(Counters)));
+    CK(cudaMemsetAsync(x->d_cnt, 0, sizeof(Counters), x->stream));
+    CK(cudaMallocHost((void**)&x->h_cnt, sizeof(Counters)));
+    memset(x->h_cnt, 0, sizeof(Counters));
+    CK(cudaMalloc((void**)&x->d_cnt_all, sizeof(Counters) * 8));
+    CK(cudaMallocHost((void**)&x->h_cnt_all, sizeof(Counters) * 8));
+    t.cnt = x->d_cnt;
+    t.shard_bits = shard_bits; t.shard_rank = c.shard_count > 1 ? c.shard_rank : 0;
+    for (int i = 0; i < 8; ++i) { t.req_peer[i] = nullptr; t.eng_peer[i] = nullptr; t.cnt_peer[i] = nullptr; }
+    t.req_peer[t.shard_rank] = t.req; t.eng_peer[t.shard_rank] = t.eng; t.cnt_peer[t.shard_rank] = t.cnt;
+    CK(cudaStreamSynchronize(x->stream));
+    if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
+    if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : !strcmp(k, "classes") ? 3 : !strcmp(k, "coop") ? 4 : 0;
+    if (const char* k = getenv("KVIDX_COOP_MAX")) x->coop_max = atoll(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
+    if (const char* k = getenv("KVIDX_CLASSES_MIN")) x->classes_min = atoll(k);
+    if (const char* k = getenv("KVIDX_CLASSES_SHARING")) x->classes_min_sharing = atof(k);
+    if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_GRID")) sscanf(k, "%d,%d,%d,%d,%d", &x->rounds_grid[0], &x->rounds_grid[1], &x->rounds_grid[2], &x->rounds_grid[3], &x->rounds_grid[4]);
+    if (const char* k = getenv("KVIDX_HOST_CHUNK_TOKENS")) x->host_chunk_tokens = std::max<int64_t>(1 << 16, atoll(k));
+    if (const char* k = getenv("KVIDX_ROUNDS_TRACE")) x->rounds_trace = atoi(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
+    if (const char* k = getenv("KVIDX_WRITE_PHASE1")) x->write_phase1 = atoi(k);
+    if (const char* k = getenv("KVIDX_GROUP_TMA")) x->group_tma = atoi(k) != 0;
+    x->queue = new_submit_queue();
+    if (rounds_init() || plain::rounds_init() || coop_init()) return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (score_tuned_init()) return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+}  // namespace
+
 int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
     if (!out) return fail(KVIDX_EINVAL, "out is NULL");
     *out = nullptr;
@@ -647,74 +1004,15 @@ int kvidx_create(const kvidx_config_t* cfg_in, kvidx_t** out) {
         return fail(KVIDX_ECUDA, "no CUDA device: libkvidx has no CPU fallback");
     }
     if (c.device < 0 || c.device >= ndev) return fail(KVIDX_EINVAL, "device %d out of range (%d devices)", c.device, ndev);
-    CK(cudaSetDevice(c.device));
     kvidx* x = new kvidx();
-    x->cfg = c;
-    x->device = c.device;
-    cudaDeviceProp prop{};
-    CK(cudaGetDeviceProperties(&prop, c.device));
-    x->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) { delete x; return fail(KVIDX_ECUDA, "device sm_%d%d is not Blackwell; libkvidx is built for sm_100a only", prop.major, prop.minor); }
-    CK(cudaStreamCreateWithFlags(&x->own_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&x->copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&x->d2h_stream, cudaStreamNonBlocking));
-    for (int q = 0; q < kMaxParts - 1; ++q) {
-        CK(cudaStreamCreateWithFlags(&x->aux_stream[q], cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&x->ev_join[q], cudaEventDisableTiming));
+    const int rc = create_impl(c, x);
+    if (rc) {                       // whatever was created so far (streams, events, tables) goes away with the handle
+        const std::string keep = g_err;
+        kvidx_destroy(x);
+        cudaGetLastError();
+        g_err = keep;
+        return rc;
     }
-    CK(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
-    x->stream = x->own_stream;
-    for (int i = 0; i < 2; ++i) {
-        CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&x->ev_done[i], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&x->ev_k[i], cudaEventDisableTiming));
-    }
-    uint32_t shard_bits = 0;
-    if (c.shard_count > 1) {
-        if (c.shard_count > 8 || (c.shard_count & (c.shard_count - 1)) || c.shard_rank >= c.shard_count) { delete x; return fail(KVIDX_EINVAL, "shard_count must be a power of two <= 8 and shard_rank < shard_count"); }
-        while ((1u << shard_bits) < c.shard_count) ++shard_bits;
-    }
-    const uint64_t per_shard = c.shard_count > 1 ? (c.capacity + c.shard_count - 1) / c.shard_count : c.capacity;
-    uint64_t slots = c.table_slots ? pow2ceil(c.table_slots) : pow2ceil(std::max<uint64_t>(4 * per_shard, 1024));
-    if (slots < 1024) slots = 1024;
-    TableView& t = x->tv;
-    t.req_mask = slots - 1; t.eng_mask = slots - 1;
-    t.capacity = c.capacity; t.init_hash = c.init_hash; t.block_size = c.block_size; t.pods_per_key = c.pods_per_key;
-    t.max_pods = c.max_pods; t.filter_words = (c.max_pods + 63) / 64;
-    for (int i = 0; i < 16; ++i) t.weight[i] = (uint32_t)i < c.n_tier_weights ? c.tier_weight[i] : 1.0;
-    t.req_stamp = nullptr;
-    int rc = alloc_tables(x, slots, slots, &t.req, &t.eng);
-    if (rc) { delete x; return rc; }
-    if (c.lru_exact) {
-        if (c.shard_count > 1) { delete x; return fail(KVIDX_EINVAL, "lru_exact is not supported on a sharded index"); }
-        CK(cudaMalloc((void**)&t.req_stamp, slots * 8));
-        CK(cudaMemsetAsync(t.req_stamp, 0, slots * 8, x->stream));
-    }
-    CK(cudaMalloc((void**)&x->d_cnt, sizeof(Counters)));
-    CK(cudaMemsetAsync(x->d_cnt, 0, sizeof(Counters), x->stream));
-    CK(cudaMallocHost((void**)&x->h_cnt, sizeof(Counters)));
-    memset(x->h_cnt, 0, sizeof(Counters));
-    t.cnt = x->d_cnt;
-    t.shard_bits = shard_bits; t.shard_rank = c.shard_count > 1 ? c.shard_rank : 0;
-    for (int i = 0; i < 8; ++i) { t.req_peer[i] = nullptr; t.eng_peer[i] = nullptr; t.cnt_peer[i] = nullptr; }
-    t.req_peer[t.shard_rank] = t.req; t.eng_peer[t.shard_rank] = t.eng; t.cnt_peer[t.shard_rank] = t.cnt;
-    CK(cudaStreamSynchronize(x->stream));
-    if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
-    if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : !strcmp(k, "classes") ? 3 : 0;
-    if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
-    if (const char* k = getenv("KVIDX_CLASSES_MIN")) x->classes_min = atoll(k);
-    if (const char* k = getenv("KVIDX_CLASSES_SHARING")) x->classes_min_sharing = atof(k);
-    if (const char* k = getenv("KVIDX_SORT_PREFIX")) x->sort_prefix = atoi(k) != 0;
-    if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP")) x->rounds_overlap = atoi(k) != 0;
-    if (const char* k = getenv("KVIDX_ROUNDS_GRID")) sscanf(k, "%d,%d,%d,%d,%d", &x->rounds_grid[0], &x->rounds_grid[1], &x->rounds_grid[2], &x->rounds_grid[3], &x->rounds_grid[4]);
-    if (const char* k = getenv("KVIDX_HOST_CHUNK_TOKENS")) x->host_chunk_tokens = std::max<int64_t>(1 << 16, atoll(k));
-    if (const char* k = getenv("KVIDX_ROUNDS_TRACE")) x->rounds_trace = atoi(k);
-    if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
-    if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);
-    if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
-    if (rounds_init() || plain::rounds_init()) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
-    rc = score_tuned_init();
-    if (rc) { delete x; return fail(KVIDX_ECUDA, "kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError())); }
     *out = x;
     return 0;
 }
@@ -723,6 +1021,7 @@ void kvidx_destroy(kvidx_t* x) {
     if (!x) return;
     cudaSetDevice(x->device);
     cudaDeviceSynchronize();
+    if (x->queue) { delete_submit_queue(x->queue); x->queue = nullptr; }
     for (int i = 0; i < 2; ++i) {
         x->d_tok[i].release(); x->d_off[i].release(); x->d_model[i].release(); x->d_filter[i].release();
         x->d_out[i].release(); x->d_aux[i].release(); x->h_stage[i].release(); x->h_out[i].release();
@@ -731,13 +1030,17 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_k[i]) cudaEventDestroy(x->ev_k[i]);
     }
     x->r_act0.release(); x->r_act1.release(); x->r_cnt.release(); x->r_hstate.release(); x->r_keys.release(); x->r_pst.release(); x->r_nbr.release(); x->r_fp.release(); x->r_sort.release(); x->r_role.release(); x->r_hl.release(); x->r_map.release(); x->r_src.release(); x->r_fate.release(); x->r_anch.release(); x->r_snap.release(); x->r_rec.release();
-    x->d_misc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
+    x->d_misc.release(); x->d_rmisc.release(); x->d_ev.release(); x->d_hash.release(); x->d_evtok.release(); x->d_qoff.release(); x->h_misc.release();
+    x->d_wkeys.release(); x->d_wpred.release(); x->d_wready.release(); x->d_wmap.release();
     if (x->tv.req) cudaFree(x->tv.req);
     if (x->tv.eng) cudaFree(x->tv.eng);
     if (x->tv.req_stamp) cudaFree(x->tv.req_stamp);
     if (x->d_cnt) cudaFree(x->d_cnt);
     if (x->h_cnt) cudaFreeHost(x->h_cnt);
+    if (x->d_cnt_all) cudaFree(x->d_cnt_all);
+    if (x->h_cnt_all) cudaFreeHost(x->h_cnt_all);
     if (x->own_stream) cudaStreamDestroy(x->own_stream);
+    if (x->own_wstream) cudaStreamDestroy(x->own_wstream);
     if (x->copy_stream) cudaStreamDestroy(x->copy_stream);
     if (x->d2h_stream) cudaStreamDestroy(x->d2h_stream);
     for (int q = 0; q < kMaxParts - 1; ++q) {
@@ -745,20 +1048,22 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_join[q]) cudaEventDestroy(x->ev_join[q]);
     }
     if (x->ev_fork) cudaEventDestroy(x->ev_fork);
+    if (x->ev_write) cudaEventDestroy(x->ev_write);
+    cudaGetLastError();
     delete x;
 }
 
 int kvidx_set_tier_weight(kvidx_t* x, uint32_t tier, double w) {
     if (!x) return fail(KVIDX_EINVAL, "NULL handle");
     if (tier >= KVIDX_MAX_TIERS) return fail(KVIDX_ERANGE, "tier %u out of range", tier);
-    std::lock_guard<std::mutex> g(x->mu);
+    std::unique_lock<std::shared_mutex> tl(x->tables);
     x->tv.weight[tier] = w;
     return 0;
 }
 
 int kvidx_set_stream(kvidx_t* x, void* s) {
     if (!x) return fail(KVIDX_EINVAL, "NULL handle");
-    std::lock_guard<std::mutex> g(x->mu);
+    ReadGuard g(x);
     x->stream = s ? static_cast<cudaStream_t>(s) : x->own_stream;
     return 0;
 }
@@ -766,6 +1071,7 @@ int kvidx_synchronize(kvidx_t* x) {
     if (!x) return fail(KVIDX_EINVAL, "NULL handle");
     CK(cudaSetDevice(x->device));
     CK(cudaStreamSynchronize(x->stream));
+    CK(cudaStreamSynchronize(x->own_wstream));
     return 0;
 }
 
@@ -782,7 +1088,7 @@ int kvidx_hash_keys(kvidx_t* x, const uint32_t* tok, const int64_t* tok_off, int
     key_off_out[n] = nk;
     if (n == 0 || nk == 0) return 0;
     if (!keys_out || !tok) return fail(KVIDX_EINVAL, "NULL buffer");
-    std::lock_guard<std::mutex> g(x->mu);
+    ReadGuard g(x);
     CK(cudaSetDevice(x->device));
     const int64_t tb = tok_off[0], nt = tok_off[n] - tb;
     CK(x->d_tok[0].need((size_t)nt * 4 + 64));
@@ -803,11 +1109,8 @@ int kvidx_hash_keys(kvidx_t* x, const uint32_t* tok, const int64_t* tok_off, int
             CK(cudaMemcpyAsync(d_pv, parent_valid, (size_t)n, cudaMemcpyHostToDevice, x->stream));
         }
     }
-    const int T = 128;
-    hash_keys_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, x->d_tok[0].as<uint32_t>(), x->d_off[0].as<int64_t>(), tb, n,
-                                                                         d_parent, d_pv, d_koff, 0, x->d_out[0].as<uint64_t>());
-    x->launches += 1;
-    CK(cudaGetLastError());
+    rc = launch_hash_keys(x, x->d_tok[0].as<uint32_t>(), x->d_off[0].as<int64_t>(), tb, n, d_parent, d_pv, d_koff, x->d_out[0].as<uint64_t>(), x->stream);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(keys_out, x->d_out[0].p, (size_t)nk * 8, cudaMemcpyDeviceToHost, x->stream));
     CK(cudaStreamSynchronize(x->stream));
     return 0;
@@ -817,13 +1120,9 @@ int kvidx_hash_keys_dev(kvidx_t* x, const uint32_t* d_tok, const int64_t* d_tok_
                         const uint8_t* d_parent_valid, const int64_t* d_key_off, uint64_t* d_keys_out) {
     if (!x || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
     if (n == 0) return 0;
-    std::lock_guard<std::mutex> g(x->mu);
+    ReadGuard g(x);
     CK(cudaSetDevice(x->device));
-    const int T = 128;
-    hash_keys_kernel_v1<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, d_tok, d_tok_off, 0, n, d_parent, d_parent_valid, d_key_off, 0, d_keys_out);
-    x->launches += 1;
-    CK(cudaGetLastError());
-    return 0;
+    return launch_hash_keys(x, d_tok, d_tok_off, 0, n, d_parent, d_parent_valid, d_key_off, d_keys_out, x->stream);
 }
 
 int kvidx_lookup(kvidx_t* x, uint32_t model, const uint64_t* keys, int64_t n, const uint64_t* filter,
@@ -832,7 +1131,7 @@ int kvidx_lookup(kvidx_t* x, uint32_t model, const uint64_t* keys, int64_t n, co
     if (n <= 0 || !keys) return fail(KVIDX_EINVAL, "no requestKeys provided for lookup");   // in_memory.go:108-110
     if (!podtier_out || !cnt_out) return fail(KVIDX_EINVAL, "NULL output");
     if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
-    std::lock_guard<std::mutex> g(x->mu);
+    ReadGuard g(x);
     CK(cudaSetDevice(x->device));
     if (int rc0 = check_shards(x)) return rc0;
     const uint32_t FW = x->tv.filter_words;
@@ -842,6 +1141,7 @@ int kvidx_lookup(kvidx_t* x, uint32_t model, const uint64_t* keys, int64_t n, co
     uint64_t* d_keys = reinterpret_cast<uint64_t*>(aux);
     uint64_t* d_f = nullptr;
     int* d_cut = reinterpret_cast<int*>(aux + (size_t)n * 8 + (size_t)FW * 8);
+    CK(cudaStreamWaitEvent(x->stream, x->ev_write, 0));
     CK(cudaMemcpyAsync(d_keys, keys, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
     if (filter) {
         d_f = reinterpret_cast<uint64_t*>(aux + (size_t)n * 8);
@@ -868,51 +1168,89 @@ int kvidx_lookup(kvidx_t* x, uint32_t model, const uint64_t* keys, int64_t n, co
 int kvidx_score_batch(kvidx_t* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
                       const uint64_t* filter, double* scores_out, uint8_t* has_keys_out) {
     if (!x || !scores_out) return fail(KVIDX_EINVAL, "bad arguments");
-    return score_host(x, tok, tok_off, n, model, model0, filter, scores_out, nullptr, nullptr, nullptr, has_keys_out);
+    return submit_score(x, tok, tok_off, n, model, model0, filter, scores_out, nullptr, nullptr, nullptr, has_keys_out);
 }
 
 int kvidx_score_batch_sparse(kvidx_t* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
                              const uint64_t* filter, uint16_t* pods_out, double* scores_out, uint8_t* cnt_out, uint8_t* has_keys_out) {
     if (!x || !pods_out || !scores_out || !cnt_out) return fail(KVIDX_EINVAL, "bad arguments");
-    return score_host(x, tok, tok_off, n, model, model0, filter, nullptr, pods_out, scores_out, cnt_out, has_keys_out);
+    return submit_score(x, tok, tok_off, n, model, model0, filter, nullptr, pods_out, scores_out, cnt_out, has_keys_out);
 }
 
 int kvidx_score_batch_dev(kvidx_t* x, const uint32_t* d_tok, const int64_t* d_tok_off, int64_t n, const uint32_t* d_model,
                           uint32_t model0, const uint64_t* d_filter, double* d_scores_out, uint8_t* d_has_keys_out) {
     if (!x || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> g(x->mu);
+    ReadGuard g(x);
     CK(cudaSetDevice(x->device));
+    CK(cudaStreamWaitEvent(x->stream, x->ev_write, 0));
     ScoreOut so{};
     so.dense = d_scores_out; so.has_keys = d_has_keys_out;
     return launch_score(x, d_tok, d_tok_off, 0, n, d_model, model0, d_filter, so, x->stream);
 }
 
+int kvidx_score_batch_sparse_dev(kvidx_t* x, const uint32_t* d_tok, const int64_t* d_tok_off, int64_t n, const uint32_t* d_model,
+                                 uint32_t model0, const uint64_t* d_filter, uint16_t* d_pods_out, double* d_scores_out,
+                                 uint8_t* d_cnt_out, uint8_t* d_has_keys_out) {
+    if (!x || n < 0 || !d_pods_out || !d_scores_out || !d_cnt_out) return fail(KVIDX_EINVAL, "bad arguments");
+    ReadGuard g(x);
+    CK(cudaSetDevice(x->device));
+    CK(cudaStreamWaitEvent(x->stream, x->ev_write, 0));
+    ScoreOut so{};
+    so.sp_pods = d_pods_out; so.sp_scores = d_scores_out; so.sp_cnt = d_cnt_out; so.has_keys = d_has_keys_out;
+    return launch_score(x, d_tok, d_tok_off, 0, n, d_model, model0, d_filter, so, x->stream);
+}
+
 // ---- write path -----------------------------------------------------------------------------
+
+namespace {
+int check_podtiers(kvidx* x, const kvidx_podtier_t* pts, int32_t m) {
+    // dense score rows and filter rows are max_pods wide: a pod id beyond that cannot be scored or filtered
+    for (int32_t j = 0; j < m; ++j)
+        if (KVIDX_PT_POD(pts[j]) >= x->tv.max_pods) return fail(KVIDX_ERANGE, "pod id %u >= max_pods %u", KVIDX_PT_POD(pts[j]), x->tv.max_pods);
+    return 0;
+}
+}  // namespace
 
 int kvidx_add(kvidx_t* x, uint32_t model, const uint64_t* engine, const uint64_t* request, int64_t n,
               const kvidx_podtier_t* pts, int32_t m) {
     if (!x) return fail(KVIDX_EINVAL, "NULL handle");
     if (n <= 0 || m <= 0 || !engine || !request || !pts) return fail(KVIDX_EINVAL, "no keys or entries provided for adding to index");
     if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
-    std::lock_guard<std::mutex> g(x->mu);
+    if (int rc0 = check_podtiers(x, pts, m)) return rc0;
+    std::lock_guard<std::mutex> g(x->mu_w);
     CK(cudaSetDevice(x->device));
     if (int rc0 = check_shards(x)) return rc0;
     int rc = ensure_room(x, (uint64_t)n);
     if (rc) return rc;
-    CK(x->d_misc.need((size_t)n * 16 + (size_t)m * 2 + 16));
+    std::shared_lock<std::shared_mutex> tl(x->tables);
+    cudaStream_t st = wstream(x);
+    CK(x->d_misc.need((size_t)n * 17 + (size_t)m * 2 + 32));
+    CK(x->h_misc.need((size_t)n + 16));
+    // pairs are added in order (in_memory.go:159): an engine key that appears again later in the call keeps the later mapping
+    uint8_t* skip = x->h_misc.as<uint8_t>();
+    bool any_dup = false;
+    {
+        std::unordered_map<uint64_t, int64_t> last;
+        last.reserve((size_t)n * 2);
+        for (int64_t i = 0; i < n; ++i) { skip[i] = 0; auto it = last.find(engine[i]); if (it != last.end()) { skip[it->second] = 1; any_dup = true; it->second = i; } else last.emplace(engine[i], i); }
+    }
     uint8_t* d = x->d_misc.as<uint8_t>();
-    CK(cudaMemcpyAsync(d, engine, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
-    CK(cudaMemcpyAsync(d + (size_t)n * 8, request, (size_t)n * 8, cudaMemcpyHostToDevice, x->stream));
-    CK(cudaMemcpyAsync(d + (size_t)n * 16, pts, (size_t)m * 2, cudaMemcpyHostToDevice, x->stream));
+    uint8_t* d_skip = d + (size_t)n * 16 + (((size_t)m * 2 + 15) & ~(size_t)15);
+    CK(cudaMemcpyAsync(d, engine, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + (size_t)n * 8, request, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + (size_t)n * 16, pts, (size_t)m * 2, cudaMemcpyHostToDevice, st));
+    if (any_dup) CK(cudaMemcpyAsync(d_skip, skip, (size_t)n, cudaMemcpyHostToDevice, st));
     const int T = 128;
-    add_kernel<<<(unsigned)((n + T - 1) / T), T, 0, x->stream>>>(x->tv, model, reinterpret_cast<uint64_t*>(d),
-                                                                reinterpret_cast<uint64_t*>(d + (size_t)n * 8), n,
-                                                                reinterpret_cast<uint16_t*>(d + (size_t)n * 16), m,
-                                                                reserve_stamps(x, 2ull * (unsigned long long)n + 2));
+    add_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x->tv, model, reinterpret_cast<uint64_t*>(d),
+                                                         reinterpret_cast<uint64_t*>(d + (size_t)n * 8), n,
+                                                         reinterpret_cast<uint16_t*>(d + (size_t)n * 16), m, any_dup ? d_skip : nullptr,
+                                                         reserve_stamps(x, 2ull * (unsigned long long)n + 2));
     x->launches += 1;
     CK(cudaGetLastError());
+    const unsigned long long nospc_before = x->h_cnt->nospc;
     rc = refresh_counters(x);
     if (rc) return rc;
+    if (x->h_cnt->nospc != nospc_before) return fail(KVIDX_ENOSPC, "%llu inserts refused: the owning shard is full", x->h_cnt->nospc - nospc_before);
     return enforce_caps(x);
 }
 
@@ -920,12 +1258,15 @@ int kvidx_evict(kvidx_t* x, uint32_t model, uint64_t engine, const kvidx_podtier
     if (!x) return fail(KVIDX_EINVAL, "NULL handle");
     if (m <= 0 || !pts) return fail(KVIDX_EINVAL, "no entries provided for eviction from index");
     if (model > 0xffffu) return fail(KVIDX_ERANGE, "model id %u > 65535", model);
-    std::lock_guard<std::mutex> g(x->mu);
+    if (int rc0 = check_podtiers(x, pts, m)) return rc0;
+    std::lock_guard<std::mutex> g(x->mu_w);
     CK(cudaSetDevice(x->device));
     if (int rc0 = check_shards(x)) return rc0;
+    std::shared_lock<std::shared_mutex> tl(x->tables);
+    cudaStream_t st = wstream(x);
     CK(x->d_misc.need((size_t)m * 2 + 16));
-    CK(cudaMemcpyAsync(x->d_misc.p, pts, (size_t)m * 2, cudaMemcpyHostToDevice, x->stream));
-    evict_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, x->d_misc.as<uint16_t>(), m, reserve_stamps(x, 4));
+    CK(cudaMemcpyAsync(x->d_misc.p, pts, (size_t)m * 2, cudaMemcpyHostToDevice, st));
+    evict_kernel<<<1, 32, 0, st>>>(x->tv, model, engine, x->d_misc.as<uint16_t>(), m, reserve_stamps(x, 4));
     x->launches += 1;
     CK(cudaGetLastError());
     return refresh_counters(x);
@@ -933,12 +1274,13 @@ int kvidx_evict(kvidx_t* x, uint32_t model, uint64_t engine, const kvidx_podtier
 
 int kvidx_get_request_key(kvidx_t* x, uint32_t model, uint64_t engine, uint64_t* out) {
     if (!x || !out) return fail(KVIDX_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> g(x->mu);
+    ReadGuard g(x);
     CK(cudaSetDevice(x->device));
     if (int rc0 = check_shards(x)) return rc0;
-    CK(x->d_misc.need(32));
-    uint64_t* d_out = x->d_misc.as<uint64_t>();
+    CK(x->d_rmisc.need(32));
+    uint64_t* d_out = x->d_rmisc.as<uint64_t>();
     int* d_found = reinterpret_cast<int*>(d_out + 1);
+    CK(cudaStreamWaitEvent(x->stream, x->ev_write, 0));
     get_request_key_kernel<<<1, 32, 0, x->stream>>>(x->tv, model, engine, d_out, d_found, x->tv.req_stamp ? reserve_stamps(x, 1) : 0);
     x->launches += 1;
     CK(cudaGetLastError());
@@ -950,18 +1292,58 @@ int kvidx_get_request_key(kvidx_t* x, uint32_t model, uint64_t engine, uint64_t*
     return 0;
 }
 
-int kvidx_apply_events_dev(kvidx_t* x, const kvidx_event_t* d_ev_sorted, const int64_t* d_queue_off, int64_t n_queues,
-                           const uint64_t* d_hashes, const uint32_t* d_tokens, int64_t* d_n_dropped) {
-    if (!x || n_queues < 0) return fail(KVIDX_EINVAL, "bad arguments");
-    if (n_queues == 0) return 0;
-    (void)d_n_dropped;
-    CK(cudaSetDevice(x->device));
+namespace {
+// Both phases of a device-resident, pod-sorted event batch on the write stream (kernels_write.cuh).  Caller holds mu_w and
+// `tables` shared.
+int launch_apply_events(kvidx* x, const kvidx_event_t* d_ev_sorted, const int64_t* d_queue_off, int64_t n_queues, int64_t n_events,
+                        const uint64_t* d_hashes, int64_t n_hashes, const uint32_t* d_tokens, cudaStream_t st) {
+    const uint64_t* d_keys = nullptr; const uint64_t* d_pred = nullptr;
+    const bool phase1 = x->write_phase1 == 1 || (x->write_phase1 < 0 && n_hashes >= x->write_phase1_min);
+    if (phase1 && n_hashes > 0) {
+        const uint64_t map_slots = pow2ceil((uint64_t)std::max<int64_t>(2 * n_events, 64));
+        CK(x->d_wkeys.need((size_t)n_hashes * 8));
+        CK(x->d_wpred.need((size_t)n_events * 8));
+        CK(x->d_wready.need((size_t)n_events * 4 + 16));
+        CK(x->d_wmap.need((size_t)map_slots * sizeof(WantEnt)));
+        unsigned int* d_ready = x->d_wready.as<unsigned int>() + 4;
+        unsigned long long* d_next = x->d_wready.as<unsigned long long>();
+        CK(cudaMemsetAsync(x->d_wready.p, 0, (size_t)n_events * 4 + 16, st));
+        CK(cudaMemsetAsync(x->d_wmap.p, 0, (size_t)map_slots * sizeof(WantEnt), st));
+        const int T = 256;
+        want_parents_kernel<<<(unsigned)((n_events + T - 1) / T), T, 0, st>>>(d_ev_sorted, n_events, x->tv.block_size, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1));
+        offer_blocks_kernel<<<(unsigned)((n_events * 32 + T - 1) / T), T, 0, st>>>(d_ev_sorted, n_events, x->tv.block_size, d_hashes, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1));
+        const int64_t ctas = std::min<int64_t>((n_events + kHashEvThreads - 1) / kHashEvThreads, (int64_t)x->sm_count * 8);
+        hash_events_kernel<<<(unsigned)ctas, kHashEvThreads, 0, st>>>(x->tv, d_ev_sorted, n_events, d_hashes, d_tokens, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1),
+                                                                     x->d_wkeys.as<uint64_t>(), x->d_wpred.as<uint64_t>(), d_ready, d_next);
+        x->launches += 3;
+        CK(cudaGetLastError());
+        d_keys = x->d_wkeys.as<uint64_t>(); d_pred = x->d_wpred.as<uint64_t>();
+    }
     const int T = 128;   // 4 queues per CTA
-    const int64_t warps = n_queues;
-    apply_events_kernel<<<(unsigned)((warps * 32 + T - 1) / T), T, 0, x->stream>>>(x->tv, d_ev_sorted, d_queue_off, n_queues, d_hashes, d_tokens,
-                                                                                    x->tv.req_stamp ? reserve_stamps(x, (1ull << 20) * (unsigned long long)x->last_batch_events) : 0);
+    apply_events_kernel<<<(unsigned)((n_queues * 32 + T - 1) / T), T, 0, st>>>(x->tv, d_ev_sorted, d_queue_off, n_queues, d_hashes, d_tokens, d_keys, d_pred,
+                                                                               x->tv.req_stamp ? reserve_stamps(x, (1ull << 20) * (unsigned long long)std::max<int64_t>(n_events, 1)) : 0);
     x->launches += 1;
     CK(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+int kvidx_apply_events_dev(kvidx_t* x, const kvidx_event_t* d_ev_sorted, const int64_t* d_queue_off, int64_t n_queues, int64_t n_events,
+                           const uint64_t* d_hashes, int64_t n_hashes, const uint32_t* d_tokens, int64_t* d_n_dropped) {
+    if (!x || n_queues < 0 || n_events < 0 || n_hashes < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n_queues == 0 || n_events == 0) return 0;
+    std::lock_guard<std::mutex> g(x->mu_w);
+    CK(cudaSetDevice(x->device));
+    if (int rc0 = check_shards(x)) return rc0;
+    int rc = ensure_room(x, (uint64_t)n_hashes);       // every hash of the batch may be a new key
+    if (rc) return rc;
+    std::shared_lock<std::shared_mutex> tl(x->tables);
+    cudaStream_t st = wstream(x);
+    rc = launch_apply_events(x, d_ev_sorted, d_queue_off, n_queues, n_events, d_hashes, n_hashes, d_tokens, st);
+    if (rc) return rc;
+    // events dropped so far on this handle (cumulative, like the counter behind kvidx_apply_events' n_dropped_out)
+    if (d_n_dropped) CK(cudaMemcpyAsync(d_n_dropped, &x->d_cnt->dropped_events, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    CK(cudaEventRecord(x->ev_write, st));              // reads issued after this call are ordered after the batch
     return 0;
 }
 
@@ -978,6 +1360,7 @@ int kvidx_apply_events(kvidx_t* x, const kvidx_event_t* ev, int64_t n, const uin
         const kvidx_event_t& e = ev[i];
         if (e.op > KVIDX_EV_BLOCK_REMOVED) return fail(KVIDX_EINVAL, "event %lld: unknown op %u", (long long)i, e.op);
         if (e.model > 0xffffu) return fail(KVIDX_ERANGE, "event %lld: model id %u > 65535", (long long)i, e.model);
+        if (KVIDX_PT_POD(e.podtier) >= x->tv.max_pods) return fail(KVIDX_ERANGE, "event %lld: pod id %u >= max_pods %u", (long long)i, KVIDX_PT_POD(e.podtier), x->tv.max_pods);
         if (e.hash_off + e.n_hashes > (uint64_t)n_hashes) return fail(KVIDX_EINVAL, "event %lld: hashes out of range", (long long)i);
         if (e.op == KVIDX_EV_BLOCK_STORED) {
             if (e.tok_off + e.n_tokens > (uint64_t)n_tokens) return fail(KVIDX_EINVAL, "event %lld: tokens out of range", (long long)i);
@@ -985,11 +1368,13 @@ int kvidx_apply_events(kvidx_t* x, const kvidx_event_t* ev, int64_t n, const uin
         }
         qcount[KVIDX_PT_POD(e.podtier) + 1]++;
     }
-    std::lock_guard<std::mutex> g(x->mu);
+    std::lock_guard<std::mutex> g(x->mu_w);
     CK(cudaSetDevice(x->device));
     if (int rc0 = check_shards(x)) return rc0;
     int rc = ensure_room(x, new_keys);
     if (rc) return rc;
+    std::shared_lock<std::shared_mutex> tl(x->tables);
+    cudaStream_t st = wstream(x);
     // compact non-empty queues
     std::vector<int64_t> start(KVIDX_MAX_PODS + 1, 0);
     for (uint32_t p = 0; p < KVIDX_MAX_PODS; ++p) start[p + 1] = start[p] + qcount[p + 1];
@@ -1006,25 +1391,26 @@ int kvidx_apply_events(kvidx_t* x, const kvidx_event_t* ev, int64_t n, const uin
     CK(x->d_ev.need((size_t)n * sizeof(kvidx_event_t)));
     CK(x->d_qoff.need((size_t)(nq + 1) * 8));
     CK(x->d_hash.need((size_t)std::max<int64_t>(n_hashes, 1) * 8));
-    CK(x->d_evtok.need((size_t)std::max<int64_t>(n_tokens, 1) * 4));
-    CK(cudaMemcpyAsync(x->d_ev.p, sorted, (size_t)n * sizeof(kvidx_event_t), cudaMemcpyHostToDevice, x->stream));
-    CK(cudaMemcpyAsync(x->d_qoff.p, qoff, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, x->stream));
-    if (n_hashes > 0) CK(cudaMemcpyAsync(x->d_hash.p, hashes, (size_t)n_hashes * 8, cudaMemcpyHostToDevice, x->stream));
-    if (n_tokens > 0) CK(cudaMemcpyAsync(x->d_evtok.p, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, x->stream));
-    const unsigned long long dropped_before = x->h_cnt->dropped_events;
+    CK(x->d_evtok.need((size_t)std::max<int64_t>(n_tokens, 1) * 4 + 16));
+    CK(cudaMemcpyAsync(x->d_ev.p, sorted, (size_t)n * sizeof(kvidx_event_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(x->d_qoff.p, qoff, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_hashes > 0) CK(cudaMemcpyAsync(x->d_hash.p, hashes, (size_t)n_hashes * 8, cudaMemcpyHostToDevice, st));
+    if (n_tokens > 0) CK(cudaMemcpyAsync(x->d_evtok.p, tokens, (size_t)n_tokens * 4, cudaMemcpyHostToDevice, st));
+    const unsigned long long dropped_before = x->h_cnt->dropped_events, nospc_before = x->h_cnt->nospc;
     x->last_batch_events = n;
-    rc = kvidx_apply_events_dev(x, x->d_ev.as<kvidx_event_t>(), x->d_qoff.as<int64_t>(), nq, x->d_hash.as<uint64_t>(),
-                                x->d_evtok.as<uint32_t>(), nullptr);
+    rc = launch_apply_events(x, x->d_ev.as<kvidx_event_t>(), x->d_qoff.as<int64_t>(), nq, n, x->d_hash.as<uint64_t>(), n_hashes,
+                             x->d_evtok.as<uint32_t>(), st);
     if (rc) return rc;
     rc = refresh_counters(x);
     if (rc) return rc;
     if (n_dropped_out) *n_dropped_out = (int64_t)(x->h_cnt->dropped_events - dropped_before);
+    if (x->h_cnt->nospc != nospc_before) return fail(KVIDX_ENOSPC, "%llu inserts refused: the owning shard is full", x->h_cnt->nospc - nospc_before);
     return enforce_caps(x);
 }
 
 int kvidx_shard_export(kvidx_t* x, void* out) {
     if (!x || !out) return fail(KVIDX_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> g(x->mu);
+    std::lock_guard<std::mutex> g(x->mu_w);
     CK(cudaSetDevice(x->device));
     cudaIpcMemHandle_t h[3];
     CK(cudaIpcGetMemHandle(&h[0], x->tv.req));
@@ -1039,7 +1425,8 @@ int kvidx_shard_import(kvidx_t* x, uint32_t rank, const void* handle) {
     if (!x || !handle) return fail(KVIDX_EINVAL, "bad arguments");
     if (rank >= (1u << x->tv.shard_bits)) return fail(KVIDX_ERANGE, "rank %u outside shard_count", rank);
     if (rank == x->tv.shard_rank) return 0;
-    std::lock_guard<std::mutex> g(x->mu);
+    std::lock_guard<std::mutex> g(x->mu_w);
+    std::unique_lock<std::shared_mutex> tl(x->tables);
     CK(cudaSetDevice(x->device));
     cudaIpcMemHandle_t h[3];
     memcpy(h, handle, sizeof h);
@@ -1056,7 +1443,8 @@ int kvidx_shard_attach(kvidx_t* x, uint32_t rank, kvidx_t* other) {
     if (rank == x->tv.shard_rank) return 0;
     if (other->tv.req_mask != x->tv.req_mask || other->tv.shard_bits != x->tv.shard_bits || other->tv.shard_rank != rank)
         return fail(KVIDX_EINVAL, "shard geometry mismatch");
-    std::lock_guard<std::mutex> g(x->mu);
+    std::lock_guard<std::mutex> g(x->mu_w);
+    std::unique_lock<std::shared_mutex> tl(x->tables);
     CK(cudaSetDevice(x->device));
     if (other->device != x->device) {
         int can = 0;
@@ -1070,16 +1458,25 @@ int kvidx_shard_attach(kvidx_t* x, uint32_t rank, kvidx_t* other) {
     return 0;
 }
 
+int kvidx_shard_compact(kvidx_t* x) {
+    if (!x) return fail(KVIDX_EINVAL, "NULL handle");
+    std::lock_guard<std::mutex> g(x->mu_w);
+    std::unique_lock<std::shared_mutex> tl(x->tables);
+    CK(cudaSetDevice(x->device));
+    return rebuild(x, x->tv.shard_bits != 0);
+}
+
 int kvidx_get_stats(kvidx_t* x, kvidx_stats_t* out) {
     if (!x || !out) return fail(KVIDX_EINVAL, "bad arguments");
-    std::lock_guard<std::mutex> g(x->mu);
+    std::lock_guard<std::mutex> g(x->mu_w);
     CK(cudaSetDevice(x->device));
     int rc = refresh_counters(x);
     if (rc) return rc;
     out->request_keys = x->h_cnt->req_full; out->engine_keys = x->h_cnt->eng_full;
     out->request_tombs = x->h_cnt->req_tomb; out->engine_tombs = x->h_cnt->eng_tomb;
     out->request_slots = x->tv.req_mask + 1; out->engine_slots = x->tv.eng_mask + 1;
-    out->rebuilds = x->rebuilds; out->kernel_launches = x->launches;
+    out->rebuilds = x->rebuilds; out->kernel_launches = x->launches.load();
+    out->rehashed_events = x->h_cnt->rehashed; out->coalesced_calls = x->queue ? submit_queue_coalesced(x->queue) : 0;
     return 0;
 }
 

@@ -129,6 +129,7 @@ struct kvhost {
     std::mutex mu;
     std::vector<std::deque<Msg>> queues;
     uint32_t filter_words = 4;
+    uint32_t pod_cap = 256;                          // == index.max_pods: ids of pods that own entries
     kvhost_metrics_t met{};              // guarded by mu
 };
 
@@ -276,6 +277,7 @@ int kvhost_create(const kvhost_config_t* cfg_in, const char* hash_seed, kvhost_t
     c.index.n_tier_weights = c.n_tiers;
     for (uint32_t i = 0; i < KVIDX_MAX_TIERS; ++i) c.index.tier_weight[i] = i < c.n_tiers ? c.tier_weights[i] : 1.0;
     h->filter_words = ((c.index.max_pods ? c.index.max_pods : 256) + 63) / 64;
+    h->pod_cap = c.index.max_pods ? c.index.max_pods : 256;     // pods that own index entries must fit the score / filter row width
     if (!c.no_device) {
         const int rc = kvidx_create(&c.index, &h->ix);
         if (rc) { g_herr = kvidx_last_error(nullptr); delete h; return rc; }
@@ -390,7 +392,7 @@ int kvhost_get_pod_scores(kvhost_t* h, const uint32_t* tokens, size_t n_tokens, 
 static int entries_of(kvhost* h, const char* const* pods, const char* const* tiers, size_t n, std::vector<kvidx_podtier_t>& out) {
     out.clear();
     for (size_t i = 0; i < n; ++i) {
-        const int p = h->pods.id(pods[i], KVIDX_MAX_PODS), t = h->tiers.id(lower(tiers[i]), KVIDX_MAX_TIERS);
+        const int p = h->pods.id(pods[i], h->pod_cap), t = h->tiers.id(lower(tiers[i]), KVIDX_MAX_TIERS);
         if (p < 0 || t < 0) return hfail(KVIDX_ERANGE, "pod / tier id space exhausted");
         out.push_back(KVIDX_PODTIER(p, t));
     }
@@ -457,7 +459,7 @@ int kvhost_pool_queue_index(kvhost_t* h, const char* pod) { return (int)kvidx_qu
 int kvhost_pool_add_task(kvhost_t* h, const char* pod, const char* model, const void* payload, size_t len) {
     if (!h || !pod || !model) return hfail(KVIDX_EINVAL, "bad arguments");
     std::lock_guard<std::mutex> g(h->mu);
-    const int p = h->pods.id(pod, KVIDX_MAX_PODS), m = h->models.id(model, 65536);
+    const int p = h->pods.id(pod, h->pod_cap), m = h->models.id(model, 65536);
     if (p < 0 || m < 0) return hfail(KVIDX_ERANGE, "pod / model id space exhausted");
     h->queues[kvidx_queue_index(pod, strlen(pod), h->cfg.concurrency)].push_back(Msg{(uint32_t)p, (uint32_t)m, std::string((const char*)payload, len)});
     return 0;
@@ -497,7 +499,7 @@ int64_t kvhost_decode_event_batch(kvhost_t* h, const char* pod, const char* mode
     std::vector<kvidx_event_t> evs; std::vector<uint64_t> hashes; std::vector<uint32_t> toks;
     {
         std::lock_guard<std::mutex> g(h->mu);
-        const int p = h->pods.id(pod, KVIDX_MAX_PODS), m = h->models.id(model, 65536);
+        const int p = h->pods.id(pod, h->pod_cap), m = h->models.id(model, 65536);
         if (p < 0 || m < 0) return hfail(KVIDX_ERANGE, "pod / model id space exhausted");
         decode_batch(h, (uint32_t)p, (uint32_t)m, (const uint8_t*)payload, len, evs, hashes, toks);
     }

@@ -33,7 +33,8 @@ class Config(C.Structure):
 class Stats(C.Structure):
     """kvidx_stats_t."""
     _fields_ = [(n, C.c_uint64) for n in ("request_keys", "engine_keys", "request_tombs", "engine_tombs",
-                                          "request_slots", "engine_slots", "rebuilds", "kernel_launches")]
+                                          "request_slots", "engine_slots", "rebuilds", "kernel_launches",
+                                          "rehashed_events", "coalesced_calls")]
 
 
 EVENT_DTYPE = np.dtype([("op", "u1"), ("has_parent", "u1"), ("podtier", "<u2"), ("model", "<u4"),
@@ -69,7 +70,9 @@ SYMBOLS = {
     "kvidx_synchronize": (C.c_int, [C.c_void_p]),
     "kvidx_score_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kvidx_hash_keys_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "kvidx_apply_events_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kvidx_apply_events_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "kvidx_score_batch_sparse_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kvidx_shard_compact": (C.c_int, [C.c_void_p]),
     "kvidx_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "kvidx_shard_export": (C.c_int, [C.c_void_p, C.c_char_p]),
     "kvidx_shard_import": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p]),
@@ -187,6 +190,10 @@ class Index:
     def shard_attach(self, rank: int, other: "Index"):
         self._ck(self.L.kvidx_shard_attach(self.h, rank, other.h))
 
+    def shard_compact(self):
+        """Drop this shard's tombstones.  Collective by contract (see kvidx.dist.compact_shards)."""
+        self._ck(self.L.kvidx_shard_compact(self.h))
+
     # -- read path --
     def hash_keys(self, tok, tok_off, parent=None, parent_valid=None):
         tok = np.ascontiguousarray(tok, np.uint32)
@@ -242,6 +249,16 @@ class Index:
         """All pointers are device addresses (ints).  Asynchronous on the handle's stream."""
         self._ck(self.L.kvidx_score_batch_dev(self.h, d_tok, d_tok_off, n, d_model or None, model0, d_filter or None,
                                               d_scores, d_has_keys or None))
+
+    def score_batch_sparse_dev(self, d_tok, d_tok_off, n, d_pods, d_scores, d_cnt, d_model=0, model0=0, d_filter=0, d_has_keys=0):
+        """Sparse result rows (<= 10 (pod, score) pairs per prompt) on the device; pointers are device addresses."""
+        self._ck(self.L.kvidx_score_batch_sparse_dev(self.h, d_tok, d_tok_off, n, d_model or None, model0, d_filter or None,
+                                                     d_pods, d_scores, d_cnt, d_has_keys or None))
+
+    def apply_events_dev(self, d_ev_sorted, d_queue_off, n_queues, n_events, d_hashes, n_hashes, d_tokens, d_n_dropped=0):
+        """Device-resident, pod-sorted event batch; asynchronous on the handle's write stream."""
+        self._ck(self.L.kvidx_apply_events_dev(self.h, d_ev_sorted, d_queue_off, n_queues, n_events, d_hashes, n_hashes, d_tokens,
+                                               d_n_dropped or None))
 
     # -- write path --
     def add(self, model, engine, request, podtiers):

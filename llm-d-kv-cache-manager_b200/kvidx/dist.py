@@ -95,6 +95,14 @@ def connect_shards(ix, device=None):
     dist.barrier()
 
 
+def compact_shards(ix):
+    """Drop the tombstones of every rank's shard (kvidx_shard_compact).  Collective: a barrier either side keeps every
+    rank off the index while the shards are rewritten in place (peers keep their mappings)."""
+    dist.barrier()
+    ix.shard_compact()
+    dist.barrier()
+
+
 def events_for_rank(events, rank: int, world: int):
     """Ingest rule of the sharded mode: all events of one pod go through one rank (pod id modulo world), which keeps
     the reference's per-pod ordering (kvevents/pool.go:129-144) without any cross-GPU coordination."""

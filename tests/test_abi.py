@@ -64,13 +64,13 @@ def test_host_metrics_exposition_format():
 
 def test_abi_version_and_struct_layout():
     L = kvidx.load()
-    assert L.kvidx_abi_version() == 1
+    assert L.kvidx_abi_version() == 2
     cfg = _native.Config()
     L.kvidx_config_default(C.byref(cfg))
     assert cfg.struct_size == C.sizeof(_native.Config) == 208
     assert (cfg.block_size, cfg.pods_per_key, cfg.max_pods, cfg.n_tier_weights) == (16, 10, 256, 2)
     assert cfg.init_hash == 0xCBF29CE484222325 and (cfg.tier_weight[0], cfg.tier_weight[1]) == (1.0, 0.8)
-    assert _native.EVENT_DTYPE.itemsize == 40 and C.sizeof(_native.Stats) == 64
+    assert _native.EVENT_DTYPE.itemsize == 40 and C.sizeof(_native.Stats) == 80
 
 
 def test_host_helpers():

@@ -20,6 +20,30 @@ def test_fnv64a_vectors():
     assert ko.fnv32a(b"") == 0x811C9DC5 and ko.fnv32a(b"a") == 0xE40C292C and ko.fnv32a(b"foobar") == 0xBF9CF968
 
 
+def test_cbor_rfc8949_appendix_a_vectors():
+    """RFC 8949 Appendix A (the published CBOR examples; RFC 7049 has the same table): unsigned integers in shortest
+    form, definite-length arrays, null -- every item kind of the block payload [parent, [tokens...], nil]
+    (token_processor.go:94-103, fxamacker/cbor CanonicalEncOptions)."""
+    uints = {0: "00", 1: "01", 10: "0a", 23: "17", 24: "1818", 25: "1819", 100: "1864", 1000: "1903e8", 1000000: "1a000f4240",
+             1000000000000: "1b000000e8d4a51000", 18446744073709551615: "1bffffffffffffffff"}
+    for v, hx in uints.items():
+        assert ko.cbor_head(0, v).hex() == hx
+    assert ko.cbor_head(4, 0).hex() == "80" and ko.cbor_head(4, 3).hex() == "83" and ko.cbor_head(4, 25).hex() == "9819"
+    # [1, 2, 3] -> 83010203 ; [1, [2, 3], [4, 5]] -> 8301820203820405 ; [1..25] -> 98190102..1718181819 ; null -> f6
+    assert (ko.cbor_head(4, 3) + b"".join(ko.cbor_head(0, v) for v in (1, 2, 3))).hex() == "83010203"
+    assert (ko.cbor_head(4, 25) + b"".join(ko.cbor_head(0, v) for v in range(1, 26))).hex() == \
+        "98190102030405060708090a0b0c0d0e0f101112131415161718181819"
+    # the block payload is the Appendix A nesting [1, [2, 3], <third item>] with null (f6) as the third item
+    assert ko.cbor_block_payload(1, [2, 3]).hex() == "8301820203f6"
+    assert ko.cbor_block_payload(1000000000000, list(range(1, 26))).hex() == \
+        "831b000000e8d4a5100098190102030405060708090a0b0c0d0e0f101112131415161718181819f6"
+    # and its hash is FNV-64a over exactly those bytes, in both oracles
+    assert ko.block_hash(1, [2, 3]) == ko.fnv64a(bytes.fromhex("8301820203f6"))
+    co = COracle(block_size=2, init_hash=1)
+    keys, _ = co.hash_keys(np.array([2, 3], np.uint32), np.array([0, 2], np.int64))
+    assert int(keys[0]) == ko.fnv64a(bytes.fromhex("8301820203f6"))
+
+
 @pytest.mark.parametrize("case", KATS["cases"], ids=[c["name"] for c in KATS["cases"]])
 def test_hash_chain_kats(case):
     tp = ko.ChunkedTokenDatabase(case["block_size"], case["seed"])
