@@ -14,8 +14,11 @@ batch of synthetic 4096-token prompts.
   cpu_baseline  the C++ restatement of the reference's Go path (oracle/, kind "port") on this box's host cores,
             on a bounded sample of the same prompts against the same 10M-block index
 
-Multi-GPU (torchrun, one rank per GPU): replica mode -- every rank holds the full index (10M blocks is
-640 MB of slots), prompts are sharded across ranks, no data-path collective; "scaling": "weak".
+Multi-GPU (torchrun, one rank per GPU), "scaling": "weak" (every rank scores its own resident batch):
+  value           hash-range SHARDED index (the north-star layout): tables partitioned over the ranks, probes and slot
+                  updates over NVLink peer memory from the scoring kernels themselves
+  value_replicas  every rank holds the full index, no exchange
+  config4         (N = 8) BASELINE config #4: 100 M-block index sharded over the 8 GPUs
 """
 import argparse
 import json
@@ -239,15 +242,55 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
+def go_probe():
+    """"probe at run time, never assume".  If a Go toolchain AND the module the hash depends on
+    (fxamacker/cbor/v2 v2.7.0) are on this box, oracle/goprobe runs the reference's own hash call shape
+    (token_processor.go:94-112) over tests/golden/hash_kats.json and the result is recorded; otherwise the reason is."""
+    import shutil
+    go = shutil.which("go")
+    if not go:
+        return {"go": None, "pinned": False, "why": "no go toolchain on this box"}
+    try:
+        ver = subprocess.run([go, "version"], capture_output=True, text=True, timeout=20).stdout.strip()
+        env = dict(os.environ, GOFLAGS="-mod=mod", GOPROXY="off", GOTOOLCHAIN="local")
+        r = subprocess.run([go, "run", "."], cwd=os.path.join(ROOT, "oracle", "goprobe"), capture_output=True, text=True, timeout=120, env=env,
+                           input=open(os.path.join(ROOT, "tests", "golden", "hash_kats.json")).read())
+        if r.returncode != 0:
+            return {"go": ver, "pinned": False, "why": "go run failed (module cache without fxamacker/cbor?): " + r.stderr.strip()[-200:]}
+        res = json.loads(r.stdout)
+        return {"go": ver, "pinned": bool(res.get("all_equal")), "cases": res.get("cases"), "mismatches": res.get("mismatches")}
+    except Exception as e:      # noqa: BLE001
+        return {"go": go, "pinned": False, "why": repr(e)[:200]}
+
+
+def h2d_peak_gbs(dev):
+    """Measured pinned host -> device copy bandwidth of this rank (1 GiB, best of 5): the bound of the e2e number."""
+    import torch
+    n = 1 << 30
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h.fill_(1)
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); d.copy_(h, non_blocking=True); e1.record(); e1.synchronize()
+        best = max(best, n / (e0.elapsed_time(e1) / 1e3) / 1e9)
+    del h, d
+    return best
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import kvidx
     from kvidx import synth
+    from kvidx import dist as kd
+    from kvidx.numa import pin_to_gpu_numa
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = pin_to_gpu_numa(local) if not os.environ.get("KVIDX_BENCH_NO_NUMA") else {"pinned": False, "note": "disabled"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -258,45 +301,71 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def all_ok(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def max_ranks(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     wl = synth.Workload(CONFIG_ID, T_TOKENS, N_BLOCKS, N_PODS, BLOCK)
     Q = int(os.environ.get("KVIDX_BENCH_BATCH", str(1048576)))      # prompts resident in HBM per step (per GPU)
     QE = int(os.environ.get("KVIDX_BENCH_E2E_BATCH", str(65536)))  # prompts per e2e step (host buffers)
+    nocheck = bool(os.environ.get("KVIDX_BENCH_NOCHECK"))          # timing experiments with ablated kernels only
 
     # ---- index: filled through the write path (BlockStored events) ----
-    #   replicas (default): every rank holds the full index, prompts are sharded, no data-path collective
-    #   sharded (KVIDX_BENCH_MODE=sharded): the tables are hash-range sharded over the ranks; every rank maps its peers'
-    #     shards (CUDA IPC, one 192-byte all_gather) and probes them through NVLink peer memory from the same kernels;
-    #     each rank ingests the events of its own pods (pod % world == rank)
-    from kvidx import dist as kd
-    mode = os.environ.get("KVIDX_BENCH_MODE", "replicas") if world > 1 else "single"
-    if mode == "sharded":
-        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + (1 << 20), max_pods=wl.P, tier_weights=WEIGHTS, device=local,
-                         shard_rank=rank, shard_count=world)
-        kd.connect_shards(ix, dev)
+    #   sharded  : the north-star layout -- request / engine tables hash-range sharded over the ranks; every rank maps its
+    #              peers' shards (CUDA IPC, one 192-byte all_gather) and probes / updates them through NVLink peer memory from
+    #              the same kernels; each rank ingests the events of its own pods (pod % world == rank).  `value` at N > 1.
+    #   replicas : every rank holds the full index, prompts are sharded, no exchange at all.  `value_replicas` at N > 1.
+    if world == 1:
+        modes = ["single"]
     else:
-        ix = kvidx.Index(block_size=BLOCK, capacity=wl.n_blocks + (1 << 20), max_pods=wl.P, tier_weights=WEIGHTS, device=local)
-    t0 = time.time()
-    n_ev = 0
-    apply_s = 0.0                                    # time inside kvidx_apply_events (host arrays in, H2D + kernel), generation excluded
-    for d0 in range(0, wl.D, 4096):
-        ev, hs, tk = wl.fill_events(d0, min(wl.D, d0 + 4096))
+        m_env = os.environ.get("KVIDX_BENCH_MODE", "both")
+        modes = ["sharded", "replicas"] if m_env == "both" else [m_env]
+
+    def build_index(mode, wlx):
         if mode == "sharded":
-            ev = kd.events_for_rank(ev, rank, world)
-        ta = time.perf_counter()
-        rc, dropped = ix.apply_events(ev, hs, tk)
-        apply_s += time.perf_counter() - ta
-        assert rc == 0 and dropped == 0, (rc, dropped, ix.last_error())
-        n_ev += len(ev)
-    barrier()
-    fill_s = time.time() - t0
-    st = ix.stats()
-    if mode == "sharded":
-        tot = torch.tensor([st["request_keys"]], dtype=torch.int64, device=dev)
-        dist.all_reduce(tot)
-        assert int(tot.item()) == wl.n_blocks, (int(tot.item()), wl.n_blocks)
-    else:
-        assert st["request_keys"] == wl.n_blocks, st
-    log("[fill] %d BlockStored events -> %d request keys in %.1fs (host event generation included)" % (n_ev, st["request_keys"], fill_s))
+            ix = kvidx.Index(block_size=BLOCK, capacity=wlx.n_blocks + (1 << 20), max_pods=wlx.P, tier_weights=WEIGHTS, device=local,
+                             shard_rank=rank, shard_count=world)
+            kd.connect_shards(ix, dev)
+        else:
+            ix = kvidx.Index(block_size=BLOCK, capacity=wlx.n_blocks + (1 << 20), max_pods=wlx.P, tier_weights=WEIGHTS, device=local)
+        t0 = time.time()
+        n_ev = 0
+        apply_s = 0.0                                    # time inside kvidx_apply_events (host arrays in, H2D + kernels), generation excluded
+        for d0 in range(0, wlx.D, 4096):
+            ev, hs, tk = wlx.fill_events(d0, min(wlx.D, d0 + 4096))
+            if mode == "sharded":
+                ev = kd.events_for_rank(ev, rank, world)
+            ta = time.perf_counter()
+            rc, dropped = ix.apply_events(ev, hs, tk)
+            apply_s += time.perf_counter() - ta
+            assert rc == 0 and dropped == 0, (rc, dropped, ix.last_error())
+            n_ev += len(ev)
+        barrier()
+        fill_s = time.time() - t0
+        st = ix.stats()
+        if mode == "sharded":
+            tot = torch.tensor([st["request_keys"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(tot)
+            assert int(tot.item()) == wlx.n_blocks, (int(tot.item()), wlx.n_blocks)
+        else:
+            assert st["request_keys"] == wlx.n_blocks, st
+        log("[fill %s] %d BlockStored events -> %d request keys on this rank in %.1fs (host event generation included; %.2fs inside apply_events, %d events re-hashed)"
+            % (mode, n_ev, st["request_keys"], fill_s, apply_s, st["rehashed_events"]))
+        return ix, {"fill_s": fill_s, "apply_s": apply_s, "events": n_ev, "keys": st["request_keys"], "slots": st["request_slots"], "rehashed": st["rehashed_events"]}
+
+    built = {m: build_index(m, wl) for m in modes}
+    primary = modes[0]
+    ix, fill = built[primary]
 
     # ---- device-resident batch (rank r scores its own slice of the query stream) ----
     q_base = rank * (Q + QE) * 4
@@ -307,47 +376,55 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)          # a real (non-default) stream: the library launches on it and
     torch.cuda.set_stream(stream)                   # the CUDA events below are recorded on it
     assert stream.cuda_stream != 0
-    ix.set_stream(stream.cuda_stream)
-
-    def step_dev():
-        ix.score_batch_dev(d_tok.data_ptr(), d_off.data_ptr(), Q, d_scores.data_ptr(), d_has_keys=d_has.data_ptr())
-
-    # parity gate before timing: closed-form expectation of the generator (bit-exact f64) on the whole batch
-    step_dev()
-    torch.cuda.synchronize()
-    nocheck = bool(os.environ.get("KVIDX_BENCH_NOCHECK"))      # timing experiments with ablated kernels only
     exp = wl.expected_scores(doc[:4096], m[:4096], WEIGHTS)
-    got = d_scores[:4096].cpu().numpy()
-    assert nocheck or np.array_equal(got, exp), "score mismatch vs closed form"
-    depth_ok = (d_scores >= 0).sum(dim=1).cpu().numpy()
-    assert nocheck or np.array_equal(depth_ok, np.where(m > 0, 4, 0)), "pod-count property failed on the full batch"
 
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
-    barrier()
-    launches0 = ix.stats()["kernel_launches"]
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
-    t_all0.record(stream)
-    for a, b in evs:
-        a.record(stream)
-        step_dev()
-        b.record(stream)
-    t_all1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    launches = ix.stats()["kernel_launches"] - launches0
-    total_ms = t_all0.elapsed_time(t_all1)
-    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
-    if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    value = world * Q * args.steps / (total_ms / 1e3)
+    def parity_gate(ixx, qs=None, what=""):
+        """closed-form expectation of the generator (bit-exact f64) on 4096 prompts + the pod-count property on the whole
+        batch, on EVERY rank; the run stops unless all ranks agree."""
+        torch.cuda.synchronize()
+        n = Q if qs is None else qs
+        ok = np.array_equal(d_scores[:min(4096, n)].cpu().numpy(), exp[:min(4096, n)])
+        ok = ok and np.array_equal((d_scores[:n] >= 0).sum(dim=1).cpu().numpy(), np.where(m[:n] > 0, 4, 0))
+        ok = all_ok(ok or nocheck)
+        assert ok, "score mismatch vs closed form (%s)" % what
+        return True
+
+    def measure(mode):
+        ixx = built[mode][0]
+        ixx.set_stream(stream.cuda_stream)
+
+        def step():
+            ixx.score_batch_dev(d_tok.data_ptr(), d_off.data_ptr(), Q, d_scores.data_ptr(), d_has_keys=d_has.data_ptr())
+        d_scores.fill_(-7.0)
+        step()
+        parity_gate(ixx, what=mode)
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        launches0 = ixx.stats()["kernel_launches"]
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+        t_all0.record(stream)
+        for a, b in evs:
+            a.record(stream)
+            step()
+            b.record(stream)
+        t_all1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        launches = ixx.stats()["kernel_launches"] - launches0
+        total_ms = max_ranks(t_all0.elapsed_time(t_all1))
+        step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+        return {"value": world * Q * args.steps / (total_ms / 1e3), "total_ms": total_ms, "step_ms": step_ms, "launches": int(launches),
+                "clocks": clocks, "step": step}
+
+    res = {mode: measure(mode) for mode in modes}
+    R = res[primary]
+    value, total_ms, step_ms, launches, clocks, step_dev = R["value"], R["total_ms"], R["step_ms"], R["launches"], R["clocks"], R["step"]
 
     # smaller batches on the same resident data (fewer chains in flight, less prefix sharing per batch): the SURVEY's
     # "64K batch" regime and half a million prompts
@@ -362,67 +439,97 @@ def run_ours(args):
         for _ in range(5):
             stp()
         e1.record(stream); barrier()
-        return world * qs * 5 / (e0.elapsed_time(e1) / 1e3)
+        return world * qs * 5 / (max_ranks(e0.elapsed_time(e1)) / 1e3)
     value_64k = sub_batch(65536)
     value_512k = sub_batch(524288)
 
-    # ---- SURVEY config #5: Score() with the write path running beside it (100 K events/s: BlockStored of new documents,
-    # BlockRemoved of the ones stored one step earlier; same handle, host arrays, calls interleaved per step) ----
+    # ---- SURVEY config #5: Score() with the write path running BESIDE it.  A writer thread applies BlockStored batches of new
+    # documents and BlockRemoved batches of the ones stored a moment ago through kvidx_apply_events (its own stream; slot
+    # updates are single-image publishes the readers never wait for) at >= 100 K events/s per GPU, while this thread runs
+    # Score() steps on the resident batch.  Scores of the resident batch must stay bit-exact.
     mixed = None
     if not os.environ.get("KVIDX_BENCH_SKIP_MIXED"):
-        step_s = (total_ms / args.steps) / 1e3
-        ev_per_step = max(16, int(100000 * step_s * 2.2))             # the interleaved step is ~2x longer than the score step alone
-        docs_per_step = max(1, ev_per_step // 20)                       # ~10 stored + ~10 removed events per document
-        n_mixed = 8
+        import threading
+        docs_per_batch = 512                                             # ~5 K stored + ~5 K removed events per pair of calls
+        n_batches = 10
         churn0 = wl.D                                                   # documents beyond the indexed ones
         batches = []
-        for s_i in range(n_mixed + 1):
-            ev, hs, tk = wl.fill_events(churn0 + s_i * docs_per_step, churn0 + (s_i + 1) * docs_per_step)
-            if mode == "sharded":
+        for s_i in range(n_batches):
+            ev, hs, tk = wl.fill_events(churn0 + s_i * docs_per_batch, churn0 + (s_i + 1) * docs_per_batch)
+            if primary == "sharded":
                 ev = kd.events_for_rank(ev, rank, world)
             rm = ev.copy(); rm["op"] = 1; rm["has_parent"] = 0; rm["n_tokens"] = 0
             batches.append((ev, rm, hs, tk))
-        n_events = 0
-        torch.cuda.synchronize(); barrier()
-        t0 = time.perf_counter()
-        for s_i in range(1, n_mixed + 1):
-            ev, _, hs, tk = batches[s_i]
-            rc, dropped = ix.apply_events(ev, hs, tk); assert rc == 0 and dropped == 0
-            _, rm, hs0, tk0 = batches[s_i - 1]
-            if s_i > 1:
-                rc, dropped = ix.apply_events(rm, hs0, tk0); assert rc == 0
-                n_events += len(rm)
-            n_events += len(ev)
-            step_dev()
-        torch.cuda.synchronize(); barrier()
-        dt = time.perf_counter() - t0
-        assert nocheck or np.array_equal(d_scores[:4096].cpu().numpy(), exp), "score mismatch with the write path running"
-        mixed = {"score_prompts_per_s": world * Q * n_mixed / dt, "events_per_s": world * n_events / dt, "blocks_per_event": wl.bpe,
-                 "note": "wall clock over %d steps of [apply_events(stored), apply_events(removed), score]; scores of the resident batch "
-                         "stay bit-exact" % n_mixed}
-        # leave the index as it was: remove the last stored batch
-        ix.apply_events(batches[n_mixed][1], batches[n_mixed][2], batches[n_mixed][3])
+        target_eps = float(os.environ.get("KVIDX_BENCH_EVENTS_PER_S", "100000")) / (world if primary == "sharded" else 1)
+        stop = threading.Event()
+        wstat = {"events": 0, "busy_s": 0.0, "err": None, "t0": None, "t1": None}
 
-    # roofline of the dominant (only) kernel in the step
+        def writer():
+            try:
+                i = 0
+                wstat["t0"] = time.perf_counter()
+                while not stop.is_set():
+                    ev, rm, hs, tk = batches[i % n_batches]
+                    ta = time.perf_counter()
+                    rc, dropped = ix.apply_events(ev, hs, tk); assert rc == 0 and dropped == 0, ix.last_error()
+                    rc, dropped = ix.apply_events(rm, hs, tk); assert rc == 0, ix.last_error()
+                    wstat["busy_s"] += time.perf_counter() - ta
+                    wstat["events"] += len(ev) + len(rm)
+                    i += 1
+                    ahead = wstat["events"] / target_eps - (time.perf_counter() - wstat["t0"])     # pace to the target rate
+                    if ahead > 0:
+                        stop.wait(ahead)
+                wstat["t1"] = time.perf_counter()
+            except Exception as e:      # noqa: BLE001
+                wstat["err"] = repr(e)
+                wstat["t1"] = time.perf_counter()
+
+        th = threading.Thread(target=writer)
+        torch.cuda.synchronize(); barrier()
+        th.start()
+        time.sleep(0.05)
+        n_mixed = max(args.steps, 10)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n_mixed):
+            step_dev()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        stop.set(); th.join()
+        mixed_ms = max_ranks(e0.elapsed_time(e1))
+        assert wstat["err"] is None, wstat["err"]
+        parity_gate(ix, what="with the write path running")
+        w_el = wstat["t1"] - wstat["t0"]
+        mixed = {"score_prompts_per_s": world * Q * n_mixed / (mixed_ms / 1e3), "events_per_s": (world if primary == "sharded" else 1) * wstat["events"] / w_el,
+                 "blocks_per_event": wl.bpe, "vs_value": (world * Q * n_mixed / (mixed_ms / 1e3)) / value,
+                 "writer_busy_frac": wstat["busy_s"] / w_el,
+                 "note": "concurrent: a writer thread paces kvidx_apply_events (BlockStored then BlockRemoved batches, ~%d events per call) to the "
+                         "target rate while %d Score() steps run on the resident batch (device-timed); scores stay bit-exact" % (len(batches[0][0]), n_mixed)}
+        barrier()
+
+    # roofline of the step
     A = algorithmic_bytes(wl, m)
     peak, peak_src = measured_peak()
     kern_s = float(step_ms.mean()) / 1e3
     achieved = float(A.sum()) / kern_s / 1e9
-    traffic = ncu_traffic()
+    default_cfg = (T_TOKENS, N_BLOCKS, Q) == (4096, 10_000_000, 1048576) and primary != "sharded"
+    traffic = ncu_traffic() if default_cfg else None          # the committed ncu capture is of the default single-GPU step only
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None if traffic is None else traffic * Q,
             "peak_source": peak_src, "algorithmic_bytes_per_prompt_mean": float(A.mean()),
             "algorithmic_bytes_per_launch": float(A.sum()), "kernel_ms": float(step_ms.mean()),
-            "kernel": "one step = prefix sort + 9 rounds x 8 parts x (group_round, group_lists, hash_round, walk_round, finish_round kernels); "
+            "kernel": "one step = prefix sort + rounds x parts x (group_round [TMA chunks], group_lists, hash_round, walk_round, finish_round); "
                       "achieved = step's algorithmic bytes / step GPU time (CUDA events around all of its launches), i.e. a lower bound for "
-                      "every kernel in it; group_round_kernel (token streaming, 31 % of the step) alone runs at 71 % of DRAM peak (profiles/)",
-            "note": "the step is a chain of 9 rounds whose kernels are latency bound at this batch size (serial FNV-1a chain of the "
-                    "representatives: 1.5-2.4 us per block; dependent index loads): ~1.75 ms per step whatever the batch size; the "
-                    "marginal cost, ~3 ns per prompt, is the DRAM time of the step's measured traffic (%s KB per prompt, ncu); see DESIGN.md"
-                    % ("%.1f" % (traffic / 1e3) if traffic else "n/a")}
+                      "every kernel in it; per-kernel ncu summaries under profiles/",
+            "note": "traffic = DRAM bytes of one step from the committed ncu capture (profiles/score_step_traffic.json), default single-GPU "
+                    "configuration only; null for any other configuration"}
 
-    # ---- e2e: host pinned buffers through kvidx_score_batch (H2D + kernel + D2H inside the timed region) ----
-    ix.set_stream(0)
+    # ---- e2e: host pinned buffers through the C ABI (H2D + kernels + D2H inside the timed region) ----
+    #   headline e2e: kvidx_score_batch_sparse -- the reference's result shape (a map of <= 10 pods per prompt, indexer.go:134)
+    #   e2e_dense   : kvidx_score_batch (a dense double[max_pods] row per prompt)
+    for mode in modes:
+        built[mode][0].set_stream(0)
+    h2d_peak = h2d_peak_gbs(dev)
     e_tok_d, e_doc, e_m = device_queries(wl, q_base + Q, q_base + Q + QE, dev)
     h_tok = kvidx.pinned_array((QE * wl.T,), np.uint32)
     torch.cuda.synchronize()
@@ -430,39 +537,58 @@ def run_ours(args):
     del e_tok_d
     h_off = np.arange(0, (QE + 1) * wl.T, wl.T, dtype=np.int64)
     h_scores = kvidx.pinned_array((QE, wl.P), np.float64)
-    for _ in range(2):
-        ix.score_batch(h_tok, h_off, out=h_scores)
-    assert nocheck or np.array_equal(h_scores[:2048], wl.expected_scores(e_doc[:2048], e_m[:2048], WEIGHTS))
-    barrier()
+    sp = (kvidx.pinned_array((QE, 10), np.uint16), kvidx.pinned_array((QE, 10), np.float64), kvidx.pinned_array((QE,), np.uint8), kvidx.pinned_array((QE,), np.uint8))
+    e_exp = wl.expected_scores(e_doc[:2048], e_m[:2048], WEIGHTS)
     e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        ix.score_batch(h_tok, h_off, out=h_scores)
-    torch.cuda.synchronize()
-    e_s = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e_s = float(tt.item())
-    e2e = {"value": world * QE * e_steps / e_s, "unit": "prompts/s", "h2d_bytes_per_step": int(QE * wl.T * 4 + (QE + 1) * 8),
-           "d2h_bytes_per_step": int(QE * wl.P * 8 + QE), "batch_prompts": QE, "steps": e_steps,
-           "note": "pinned host tokens -> kvidx_score_batch -> dense f64 rows in pinned host memory"}
 
-    # ---- small-batch latency (the regime a single gRPC request sees) ----
+    def e2e_run(sparse):
+        def call():
+            if sparse:
+                ix.score_batch_sparse(h_tok, h_off, out=sp)
+            else:
+                ix.score_batch(h_tok, h_off, out=h_scores)
+        for _ in range(2):
+            call()
+        if sparse:
+            got = np.full((2048, wl.P), -1.0)
+            for i in range(2048):
+                got[i, sp[0][i, :sp[2][i]]] = sp[1][i, :sp[2][i]]
+        else:
+            got = h_scores[:2048]
+        assert all_ok(nocheck or np.array_equal(got, e_exp)), "e2e score mismatch"
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            call()
+        torch.cuda.synchronize()
+        return max_ranks(time.perf_counter() - t0)
+    h2d_b = int(QE * wl.T * 4 + (QE + 1) * 8)
+    es_s = e2e_run(True)
+    es_d = e2e_run(False)
+    e2e = {"value": world * QE * e_steps / es_s, "unit": "prompts/s", "h2d_bytes_per_step": h2d_b,
+           "d2h_bytes_per_step": int(QE * (10 * 10 + 2)), "batch_prompts": QE, "steps": e_steps,
+           "h2d_peak_GBps_this_rank": h2d_peak, "pcie_frac": (h2d_b * e_steps / es_s / 1e9) / h2d_peak,
+           "numa": numa,
+           "note": "pinned host tokens -> kvidx_score_batch_sparse -> <= 10 (pod, score) pairs per prompt in pinned host memory "
+                   "(the reference's result shape); pcie_frac = achieved H2D rate / this rank's measured pinned-copy bandwidth"}
+    e2e_dense = {"value": world * QE * e_steps / es_d, "unit": "prompts/s", "h2d_bytes_per_step": h2d_b,
+                 "d2h_bytes_per_step": int(QE * wl.P * 8 + QE), "pcie_frac": (h2d_b * e_steps / es_d / 1e9) / h2d_peak}
+
+    # ---- small-batch latency (the regime a single gRPC request sees): warp-per-prompt cooperative kernel ----
     lat = {}
     for nb in (1, 1024):
         ts = []
-        for _ in range(30):
+        for _ in range(40):
             t0 = time.perf_counter()
             ix.score_batch(h_tok[: nb * wl.T], h_off[: nb + 1], out=h_scores[:nb])
             ts.append(time.perf_counter() - t0)
-        ts = np.array(ts[5:]) * 1e3
+        ts = np.array(ts[8:]) * 1e3
         lat["batch_%d" % nb] = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99))}
+    lat["batch_1_matched_blocks"] = int(e_m[0])
 
     # ---- CPU baseline (rank 0, N=1 only): the reference-path port on the host cores ----
     cpu = None
     if rank == 0 and world == 1 and not os.environ.get("KVIDX_BENCH_SKIP_CPU"):
-        threads = host_threads()
         co, cfill = build_cpu_oracle(wl)
         ns = int(os.environ.get("KVIDX_CPU_SAMPLE", "8192"))
         threads, el, l, ref_s = best_threads(co, h_tok, h_off, ns, wl)
@@ -472,7 +598,44 @@ def run_ours(args):
                "sample": "%d of the e2e prompts, one GetPodScores per call on %d threads (best of a 1..%d sweep: the path "
                          "serialises on the LRU mutex) against the same %d-block index (bit-exact vs GPU: checked); index fill %.1fs"
                          % (ns, threads, host_threads(), wl.n_blocks, cfill), "host_cores": host_threads(),
-               "p50_latency_ms": float(np.percentile(l, 50)) / 1e6, "p99_latency_ms": float(np.percentile(l, 99)) / 1e6}
+               "p50_latency_ms": float(np.percentile(l, 50)) / 1e6, "p99_latency_ms": float(np.percentile(l, 99)) / 1e6,
+               "go_probe": go_probe()}
+        del co
+
+    # ---- BASELINE config #4 (100 M-block index hash-sharded over the 8 GPUs of the box), as an extra record at N = 8 ----
+    config4 = None
+    want_c4 = os.environ.get("KVIDX_BENCH_CONFIG4", "1" if world == 8 else "0") == "1"
+    if want_c4 and world > 1:
+        barrier()                                               # nobody is still probing a peer's shard
+        for mode in modes:
+            built[mode][0].close()
+        built.clear()
+        barrier()
+        wl4 = synth.Workload(CONFIG_ID, T_TOKENS, int(os.environ.get("KVIDX_BENCH_CONFIG4_BLOCKS", "100000000")), N_PODS, BLOCK)
+        ix4, fill4 = build_index("sharded", wl4)
+        del d_tok
+        torch.cuda.empty_cache()
+        d_tok, doc, m = device_queries(wl4, q_base, q_base + Q, dev)
+        exp = wl4.expected_scores(doc[:4096], m[:4096], WEIGHTS)
+        ix4.set_stream(stream.cuda_stream)
+
+        def step4():
+            ix4.score_batch_dev(d_tok.data_ptr(), d_off.data_ptr(), Q, d_scores.data_ptr(), d_has_keys=d_has.data_ptr())
+        d_scores.fill_(-7.0)
+        step4()
+        parity_gate(ix4, what="config #4")
+        for _ in range(3):
+            step4()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record(stream)
+        n4 = 5
+        for _ in range(n4):
+            step4()
+        e1.record(stream); barrier()
+        ms4 = max_ranks(e0.elapsed_time(e1))
+        config4 = {"value": world * Q * n4 / (ms4 / 1e3), "unit": "prompts/s", "ms_per_step": ms4 / n4, "index_blocks": wl4.n_blocks,
+                   "queries_per_document": world * Q / wl4.D, "index_fill_s": fill4["fill_s"], "apply_events_s": fill4["apply_s"], "parity": "closed form, every rank",
+                   "note": "BASELINE config #4: 100 M-block / 256-pod index hash-range sharded over %d GPUs, %d resident 4K-token prompts per GPU" % (world, Q)}
 
     if rank == 0:
         out = {"metric": "score_prompts_per_sec", "value": value, "unit": "prompts/s", "n_gpus": world, "steps": args.steps,
@@ -484,19 +647,36 @@ def run_ours(args):
                           "batch_prompts_per_gpu": Q, "query_mix": "m uniform in [0,n] matched blocks + random tail",
                           "queries_per_document": Q / wl.D,
                           "pipeline": "prefix-class rounds: each distinct prefix is hashed and probed once per batch (batches >= 393216 prompts; "
-                                      "smaller ones, and batches with little repetition, take the per-prompt round or fused kernels)"
-                                      if launches / max(args.steps, 1) > 100 else "per-prompt rounds (batch below the class pipeline's size threshold, or too "
-                                      "little repetition: fewer than ~6 prompts per distinct first block)",
-                          "l2_policy": "inputs (%.1f GB tokens + %.1f GB table) larger than the 126 MB L2; no flush" % (Q * wl.T * 4 / 1e9, st["request_slots"] * 32 / 1e9),
+                                      "smaller ones, and batches with little repetition, take the per-prompt round kernels, <= 2048 prompts the "
+                                      "warp-per-prompt cooperative kernel)"
+                                      if launches / max(args.steps, 1) > 100 else "per-prompt rounds / cooperative kernel (batch below the class pipeline's size "
+                                      "threshold, or too little repetition: fewer than ~6 prompts per distinct first block)",
+                          "l2_policy": "inputs (%.1f GB tokens + %.1f GB table) larger than the 126 MB L2; no flush" % (Q * wl.T * 4 / 1e9, fill["slots"] * 32 / 1e9),
                           "multi_gpu": {"single": "single GPU", "replicas": "replicas: full index per GPU, prompts sharded, no data-path collective",
-                                        "sharded": "hash-range sharded tables, probes over NVLink peer memory (CUDA IPC), per-pod ingest ranks"}[mode],
-                          "index_fill_s": fill_s, "fill_events": n_ev},
-               "write_path": {"apply_events_s": apply_s, "events_per_s": n_ev / apply_s, "blocks_per_s": st["request_keys"] / apply_s,
-                              "algorithmic_GBps": st["request_keys"] * 136 / apply_s / 1e9,
-                              "note": "index fill through kvidx_apply_events from host arrays (BlockStored, %d blocks per event): copy in + "
-                                      "apply_events_kernel; A_ev = 136 B per block (SURVEY 8(d))" % wl.bpe},
-               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k, "value_at_512k_batch": value_512k, "mixed_read_write": mixed,
-               "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                                        "sharded": "hash-range sharded tables (the north-star layout): probes and slot updates over NVLink peer memory "
+                                                   "from the scoring / event kernels themselves (CUDA IPC), per-pod ingest ranks; value_replicas = "
+                                                   "the replica layout on the same box"}[primary],
+                          "index_fill_s": fill["fill_s"], "fill_events": fill["events"]},
+               "parity": {"gate": "closed-form scores of 4096 prompts per rank bit-exact + pod-count property on every resident prompt, every rank, every "
+                                  "mode, before timing and again after the concurrent write run", "modes": modes, "ok": True},
+               "write_path": {"apply_events_s": fill["apply_s"], "events_per_s": fill["events"] / fill["apply_s"], "blocks_per_s": fill["keys"] / fill["apply_s"],
+                              "pod_entries_per_s": fill["keys"] * 2.5 / fill["apply_s"],
+                              "algorithmic_GBps": fill["keys"] * 136 / fill["apply_s"] / 1e9,
+                              "roofline": {"bound": "hbm", "achieved": fill["keys"] * 136 / fill["apply_s"] / 1e9, "peak": peak, "unit": "GB/s",
+                                           "frac": fill["keys"] * 136 / fill["apply_s"] / 1e9 / peak},
+                              "rehashed_events": fill["rehashed"],
+                              "note": "index fill through kvidx_apply_events from host arrays (BlockStored, %d blocks per event, 4 pods per document): "
+                                      "host sort + H2D + hash_events_kernel + apply_events_kernel, per rank; A_ev = 136 B per block (SURVEY 8(d)); "
+                                      "this rank's share of the index = %d keys" % (wl.bpe, fill["keys"])},
+               "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k, "value_at_512k_batch": value_512k,
+               "mixed_read_write": mixed, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense": e2e_dense,
+               "gpu_launches": int(launches), "clocks": clocks}
+        if "replicas" in res and primary != "replicas":
+            out["value_replicas"] = res["replicas"]["value"]
+            out["ms_per_step_replicas"] = res["replicas"]["total_ms"] / args.steps
+            out["sharded_over_replicas"] = value / res["replicas"]["value"]
+        if config4 is not None:
+            out["config4"] = config4
         emit(out)
     if world > 1:
         dist.destroy_process_group()

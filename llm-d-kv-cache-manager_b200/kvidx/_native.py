@@ -230,14 +230,18 @@ class Index:
                                           _p(filter_mask, _u64p), _p(scores, _f64p), _p(has, _u8p)))
         return scores, has
 
-    def score_batch_sparse(self, tok, tok_off, model=None, model0=0, filter_mask=None):
+    def score_batch_sparse(self, tok, tok_off, model=None, model0=0, filter_mask=None, out=None):
+        """out: optional preallocated (pods (n,10) uint16, scores (n,10) float64, cnt (n,) uint8, has (n,) uint8)."""
         tok = np.ascontiguousarray(tok, np.uint32)
         tok_off = np.ascontiguousarray(tok_off, np.int64)
         n = len(tok_off) - 1
-        pods = np.zeros((n, E), np.uint16)
-        scores = np.zeros((n, E), np.float64)
-        cnt = np.zeros(n, np.uint8)
-        has = np.zeros(n, np.uint8)
+        if out is None:
+            pods = np.zeros((n, E), np.uint16)
+            scores = np.zeros((n, E), np.float64)
+            cnt = np.zeros(n, np.uint8)
+            has = np.zeros(n, np.uint8)
+        else:
+            pods, scores, cnt, has = out
         model = None if model is None else np.ascontiguousarray(model, np.uint32)
         filter_mask = None if filter_mask is None else np.ascontiguousarray(filter_mask, np.uint64)
         self._ck(self.L.kvidx_score_batch_sparse(self.h, _p(tok, _u32p), _p(tok_off, _i64p), n, _p(model, _u32p), model0,
