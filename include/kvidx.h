@@ -239,6 +239,19 @@ int kvidx_shard_attach(kvidx_t* idx, uint32_t rank, kvidx_t* other);
  * unsharded handle it is the compaction the write path runs by itself when needed. */
 int kvidx_shard_compact(kvidx_t* idx);
 
+/* The ROUTED form of a sharded Score() (all-to-all of keys to their owners, slot images back), as three
+ * device steps around an exchange the embedding program performs (kvidx.dist.score_alltoall does it with NCCL
+ * all_to_all_single).  Provided so that the two designs can be measured against each other; the library's own sharded
+ * Score() probes the owner's shard directly from the walk (see above) and needs none of this.
+ *   key_owners : owner rank of every key (the routing decision)
+ *   probe_slots: owner side -- the 32-byte slot image of every key of THIS shard (all zero: not in the index)
+ *   score_slots: origin side -- consecutive-prefix walk + score over the returned images, prompt i owning images
+ *                d_key_off[i] .. d_key_off[i+1]; dense rows like kvidx_score_batch_dev. */
+int kvidx_key_owners_dev(kvidx_t* idx, const uint64_t* d_keys, const uint32_t* d_model, uint32_t model0, int64_t n, uint8_t* d_owner_out);
+int kvidx_probe_slots_dev(kvidx_t* idx, const uint64_t* d_keys, const uint32_t* d_model, uint32_t model0, int64_t n, void* d_slots_out);
+int kvidx_score_slots_dev(kvidx_t* idx, const void* d_slots, const int64_t* d_key_off, int64_t n_prompts, const uint64_t* d_filter,
+                          double* d_scores_out, uint8_t* d_has_keys_out);
+
 /* ---- introspection ------------------------------------------------------------ */
 typedef struct kvidx_stats {
     uint64_t request_keys;      /* resident request keys (lru data.Len())       */

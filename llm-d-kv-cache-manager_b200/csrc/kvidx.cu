@@ -23,6 +23,7 @@
 #include "kernels_rounds.cuh"
 #include "kernels_rounds_plain.cuh"
 #include "kernels_coop.cuh"
+#include "kernels_route.cuh"
 #include <cub/device/device_radix_sort.cuh>
 
 using namespace kvx;
@@ -1198,6 +1199,45 @@ int kvidx_score_batch_sparse_dev(kvidx_t* x, const uint32_t* d_tok, const int64_
     ScoreOut so{};
     so.sp_pods = d_pods_out; so.sp_scores = d_scores_out; so.sp_cnt = d_cnt_out; so.has_keys = d_has_keys_out;
     return launch_score(x, d_tok, d_tok_off, 0, n, d_model, model0, d_filter, so, x->stream);
+}
+
+// ---- routed (all-to-all) form of the sharded Score(): the device steps around the exchange (kernels_route.cuh) ----
+
+int kvidx_key_owners_dev(kvidx_t* x, const uint64_t* d_keys, const uint32_t* d_model, uint32_t model0, int64_t n, uint8_t* d_owner_out) {
+    if (!x || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    ReadGuard g(x);
+    CK(cudaSetDevice(x->device));
+    key_owners_kernel<<<(unsigned)((n + 255) / 256), 256, 0, x->stream>>>(x->tv, d_keys, d_model, model0, n, d_owner_out);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int kvidx_probe_slots_dev(kvidx_t* x, const uint64_t* d_keys, const uint32_t* d_model, uint32_t model0, int64_t n, void* d_slots_out) {
+    if (!x || n < 0) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n == 0) return 0;
+    ReadGuard g(x);
+    CK(cudaSetDevice(x->device));
+    if (int rc0 = check_shards(x)) return rc0;
+    CK(cudaStreamWaitEvent(x->stream, x->ev_write, 0));
+    probe_slots_kernel<<<(unsigned)((n + 255) / 256), 256, 0, x->stream>>>(x->tv, d_keys, d_model, model0, n, static_cast<uint4*>(d_slots_out));
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int kvidx_score_slots_dev(kvidx_t* x, const void* d_slots, const int64_t* d_key_off, int64_t n_prompts, const uint64_t* d_filter,
+                          double* d_scores_out, uint8_t* d_has_keys_out) {
+    if (!x || n_prompts < 0 || !d_scores_out) return fail(KVIDX_EINVAL, "bad arguments");
+    if (n_prompts == 0) return 0;
+    ReadGuard g(x);
+    CK(cudaSetDevice(x->device));
+    score_slots_kernel<<<(unsigned)((n_prompts + 127) / 128), 128, 0, x->stream>>>(x->tv, static_cast<const uint4*>(d_slots), d_key_off, n_prompts, d_filter,
+                                                                                   d_scores_out, d_has_keys_out);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    return 0;
 }
 
 // ---- write path -----------------------------------------------------------------------------

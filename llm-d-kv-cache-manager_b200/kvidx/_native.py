@@ -73,6 +73,9 @@ SYMBOLS = {
     "kvidx_apply_events_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "kvidx_score_batch_sparse_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kvidx_shard_compact": (C.c_int, [C.c_void_p]),
+    "kvidx_key_owners_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int64, C.c_void_p]),
+    "kvidx_probe_slots_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int64, C.c_void_p]),
+    "kvidx_score_slots_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kvidx_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "kvidx_shard_export": (C.c_int, [C.c_void_p, C.c_char_p]),
     "kvidx_shard_import": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p]),
@@ -258,6 +261,18 @@ class Index:
         """Sparse result rows (<= 10 (pod, score) pairs per prompt) on the device; pointers are device addresses."""
         self._ck(self.L.kvidx_score_batch_sparse_dev(self.h, d_tok, d_tok_off, n, d_model or None, model0, d_filter or None,
                                                      d_pods, d_scores, d_cnt, d_has_keys or None))
+
+    def hash_keys_dev(self, d_tok, d_tok_off, n, d_key_off, d_keys, d_parent=0, d_parent_valid=0):
+        self._ck(self.L.kvidx_hash_keys_dev(self.h, d_tok, d_tok_off, n, d_parent or None, d_parent_valid or None, d_key_off, d_keys))
+
+    def key_owners_dev(self, d_keys, n, d_owner, model0=0, d_model=0):
+        self._ck(self.L.kvidx_key_owners_dev(self.h, d_keys, d_model or None, model0, n, d_owner))
+
+    def probe_slots_dev(self, d_keys, n, d_slots, model0=0, d_model=0):
+        self._ck(self.L.kvidx_probe_slots_dev(self.h, d_keys, d_model or None, model0, n, d_slots))
+
+    def score_slots_dev(self, d_slots, d_key_off, n_prompts, d_scores, d_filter=0, d_has_keys=0):
+        self._ck(self.L.kvidx_score_slots_dev(self.h, d_slots, d_key_off, n_prompts, d_filter or None, d_scores, d_has_keys or None))
 
     def apply_events_dev(self, d_ev_sorted, d_queue_off, n_queues, n_events, d_hashes, n_hashes, d_tokens, d_n_dropped=0):
         """Device-resident, pod-sorted event batch; asynchronous on the handle's write stream."""

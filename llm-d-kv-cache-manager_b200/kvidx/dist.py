@@ -108,3 +108,49 @@ def events_for_rank(events, rank: int, world: int):
     the reference's per-pod ordering (kvevents/pool.go:129-144) without any cross-GPU coordination."""
     pods = events["podtier"] >> 4
     return events[(pods % world) == rank]
+
+
+def _a2a(out, inp, out_split=None, in_split=None):
+    """all_to_all_single on whatever backend the group has (gloo has no CUDA all-to-all: stage through the host there)."""
+    if dist.get_backend() == "gloo" and inp.is_cuda:
+        o = torch.empty(out.shape, dtype=out.dtype)
+        dist.all_to_all_single(o, inp.cpu(), out_split, in_split)
+        out.copy_(o)
+    else:
+        dist.all_to_all_single(out, inp, out_split, in_split)
+
+
+def score_alltoall(ix, d_tok, d_off, n, d_scores, block_size=16, model0=0, d_has=None):
+    """The ROUTED form of a sharded Score(): every key of every prompt is hashed at the origin, sent to the rank
+    that owns its hash range (NCCL all-to-all), looked up there, and its 32-byte slot image sent back (second all-to-all); the
+    origin then walks and scores.  No early exit, no prefix sharing: all n_blocks keys travel.  Tensors are torch CUDA
+    tensors; `ix` is a sharded handle whose stream is the current torch stream (ix.set_stream).  Returns a dict of volumes."""
+    world = dist.get_world_size()
+    dev = d_tok.device
+    lens = torch.div(d_off[1:n + 1] - d_off[:n], block_size, rounding_mode="floor")
+    koff = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=koff[1:])
+    nk = int(koff[-1].item())
+    keys = torch.empty(max(nk, 1), dtype=torch.int64, device=dev)
+    ix.hash_keys_dev(d_tok.data_ptr(), d_off.data_ptr(), n, koff.data_ptr(), keys.data_ptr())
+    keys = keys[:nk]
+    owners = torch.empty(max(nk, 1), dtype=torch.uint8, device=dev)
+    ix.key_owners_dev(keys.data_ptr(), nk, owners.data_ptr(), model0)
+    owners = owners[:nk]
+    order = torch.argsort(owners, stable=True)
+    counts = torch.bincount(owners, minlength=world).to(torch.int64)
+    send = keys[order].contiguous()
+    recv_counts = torch.empty_like(counts)
+    _a2a(recv_counts, counts)
+    in_split, out_split = counts.tolist(), recv_counts.tolist()
+    recv = torch.empty(sum(out_split), dtype=torch.int64, device=dev)
+    _a2a(recv, send, out_split, in_split)
+    slots = torch.empty((max(len(recv), 1), 4), dtype=torch.int64, device=dev)
+    ix.probe_slots_dev(recv.data_ptr(), len(recv), slots.data_ptr(), model0)
+    slots = slots[: len(recv)]
+    back = torch.empty((nk, 4), dtype=torch.int64, device=dev)
+    _a2a(back, slots.contiguous(), in_split, out_split)
+    slots_pm = torch.empty_like(back)
+    slots_pm[order] = back
+    ix.score_slots_dev(slots_pm.data_ptr(), koff.data_ptr(), n, d_scores.data_ptr(), d_has_keys=(d_has.data_ptr() if d_has is not None else 0))
+    return {"keys": nk, "bytes_out": 8 * (nk - in_split[dist.get_rank()]), "bytes_back": 32 * (nk - in_split[dist.get_rank()])}
