@@ -425,6 +425,14 @@ def run_ours(args):
     res = {mode: measure(mode) for mode in modes}
     R = res[primary]
     value, total_ms, step_ms, launches, clocks, step_dev = R["value"], R["total_ms"], R["step_ms"], R["launches"], R["clocks"], R["step"]
+    if os.environ.get("KVIDX_BENCH_QUICK"):                       # profiling runs (ncu): the timed steps only
+        if rank == 0:
+            emit({"metric": "score_prompts_per_sec", "value": value, "unit": "prompts/s", "n_gpus": world, "steps": args.steps, "ms_per_step": total_ms / args.steps,
+                  "gpu_launches": int(launches), "quick": True, "mode": primary, "fill": fill,
+                  "value_replicas": res["replicas"]["value"] if "replicas" in res and primary != "replicas" else None})
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # smaller batches on the same resident data (fewer chains in flight, less prefix sharing per batch): the SURVEY's
     # "64K batch" regime and half a million prompts
@@ -442,6 +450,41 @@ def run_ours(args):
         return world * qs * 5 / (max_ranks(e0.elapsed_time(e1)) / 1e3)
     value_64k = sub_batch(65536)
     value_512k = sub_batch(524288)
+
+    # ---- the two ways to run a sharded Score(): peer-memory probes from the walk (what the library does) vs the routed form
+    # of SURVEY 8(e) (NCCL all-to-all of every key to its owner, slot images back), same prompts, same index, same batch ----
+    alltoall = None
+    if world > 1 and "sharded" in built and not os.environ.get("KVIDX_BENCH_SKIP_A2A"):
+        Qa = min(Q, int(os.environ.get("KVIDX_BENCH_A2A_BATCH", "131072")))
+        ix_s = built["sharded"][0]
+        d_scores.fill_(-7.0)
+        vol = kd.score_alltoall(ix_s, d_tok, d_off, Qa, d_scores, BLOCK, d_has=d_has)
+        parity_gate(ix_s, qs=Qa, what="routed all-to-all")
+        for _ in range(2):
+            kd.score_alltoall(ix_s, d_tok, d_off, Qa, d_scores, BLOCK, d_has=d_has)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record(stream)
+        for _ in range(3):
+            kd.score_alltoall(ix_s, d_tok, d_off, Qa, d_scores, BLOCK, d_has=d_has)
+        e1.record(stream); barrier()
+        a2a_ms = max_ranks(e0.elapsed_time(e1)) / 3
+
+        def peer_step():
+            ix_s.score_batch_dev(d_tok.data_ptr(), d_off.data_ptr(), Qa, d_scores.data_ptr(), d_has_keys=d_has.data_ptr())
+        for _ in range(3):
+            peer_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); e0.record(stream)
+        for _ in range(5):
+            peer_step()
+        e1.record(stream); barrier()
+        peer_ms = max_ranks(e0.elapsed_time(e1)) / 5
+        alltoall = {"batch_prompts_per_gpu": Qa, "value_alltoall": world * Qa / (a2a_ms / 1e3), "ms_per_step_alltoall": a2a_ms,
+                    "value_peer_probes": world * Qa / (peer_ms / 1e3), "ms_per_step_peer_probes": peer_ms,
+                    "nvlink_bytes_per_prompt_alltoall": (vol["bytes_out"] + vol["bytes_back"]) / Qa,
+                    "note": "routed form: every key of every prompt hashed at the origin, 8 B to its owner and 32 B back through two NCCL "
+                            "all_to_all_single calls, no early exit, no prefix sharing; peer probes: the library's sharded path (64-byte peer loads "
+                            "issued by the walk for the slots it actually visits). Both bit-exact vs the closed form."}
 
     # ---- SURVEY config #5: Score() with the write path running BESIDE it.  A writer thread applies BlockStored batches of new
     # documents and BlockRemoved batches of the ones stored a moment ago through kvidx_apply_events (its own stream; slot
@@ -675,6 +718,8 @@ def run_ours(args):
             out["value_replicas"] = res["replicas"]["value"]
             out["ms_per_step_replicas"] = res["replicas"]["total_ms"] / args.steps
             out["sharded_over_replicas"] = value / res["replicas"]["value"]
+        if alltoall is not None:
+            out["alltoall_vs_peer_probes"] = alltoall
         if config4 is not None:
             out["config4"] = config4
         emit(out)

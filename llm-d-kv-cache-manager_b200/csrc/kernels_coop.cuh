@@ -48,34 +48,54 @@ struct CoopSmem {
     } w[kCoopWarps];
 };
 
+// ballot of "bit `bit` of z is set" (LOP3 with predicate output + VOTE)
+__device__ __forceinline__ uint32_t ballot_bit(uint32_t z, uint32_t bit) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(r) : "r"(z), "r"(bit));
+    return r;
+}
+
 // One 16-token block, all 32 lanes together.  parent >= 2^32 (9-byte CBOR head); payload = 0x83, 0x1b, 8 parent bytes,
-// 0x90, tb token bytes, 0xf6.  bK0..2 are this lane's payload bytes at positions lane, lane+32, lane+64 wherever they do not
-// depend on the parent (0 where the position is past the payload), vmask bit g says position lane+32g is inside it.
+// 0x90, tb token bytes, 0xf6: n = tb + 12 bytes.  Lane l owns the three CONSECUTIVE positions 3l, 3l+1, 3l+2 (b0..b2: the
+// bytes there as far as they do not depend on the parent -- 0 past the payload; vmask bit i: position 3l+i is inside it).
+// Per bit plane k: every position contributes g = bit k of (b ^ carry); the lane's exclusive prefix parity over all earlier
+// positions is ONE ballot of the lanes' parities + a popcount, the two steps inside the lane are register XORs.
 __device__ __forceinline__ uint64_t coop_hash_block(const CoopTables& tab, uint64_t parent, uint32_t tb, uint32_t b0, uint32_t b1, uint32_t b2,
                                                     uint32_t vmask, int lane, uint32_t lt) {
-    if (lane >= 2 && lane <= 9) b0 = (uint32_t)(parent >> (8 * (9 - lane))) & 0xffu;
+    if (lane < 4) {                                         // positions 2..9 carry the parent, most significant byte first
+        const uint32_t ph = (uint32_t)(parent >> 32), pl = (uint32_t)parent;
+        if (lane == 0) b2 = ph >> 24;
+        else if (lane == 1) { b0 = (ph >> 16) & 0xffu; b1 = (ph >> 8) & 0xffu; b2 = ph & 0xffu; }
+        else if (lane == 2) { b0 = pl >> 24; b1 = (pl >> 16) & 0xffu; b2 = (pl >> 8) & 0xffu; }
+        else b0 = pl & 0xffu;
+    }
+    constexpr uint32_t L0 = (uint32_t)(kFnvOffset & 0xffu);
+    const uint32_t bs = b0 ^ b1 ^ b2;
+    // Y_i = (x_i mod 2^k) * 0xb3: its bit k is the carry into plane k;  X_i accumulates x_i = L_i ^ b_i
     uint32_t X0 = 0, X1 = 0, X2 = 0, Y0 = 0, Y1 = 0, Y2 = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const uint32_t bit = 1u << k, l0 = (uint32_t)(kFnvOffset & 0xffu) & bit;
-        const uint32_t B0 = __ballot_sync(0xffffffffu, ((b0 ^ Y0) & bit) != 0u);
-        const uint32_t B1 = __ballot_sync(0xffffffffu, ((b1 ^ Y1) & bit) != 0u);
-        const uint32_t B2 = __ballot_sync(0xffffffffu, ((b2 ^ Y2) & bit) != 0u);
-        const uint32_t p0 = (uint32_t)__popc(B0 & lt), p1 = (uint32_t)__popc((B1 & lt) ^ B0), p2 = (uint32_t)__popc((B2 & lt) ^ B0 ^ B1);
-        const uint32_t t0 = ((p0 << k) ^ b0 ^ l0) & bit, t1 = ((p1 << k) ^ b1 ^ l0) & bit, t2 = ((p2 << k) ^ b2 ^ l0) & bit;
+        const uint32_t bit = 1u << k;
+        const uint32_t z0 = b0 ^ Y0, z01 = z0 ^ b1 ^ Y1;                      // g0, g0^g1 at bit k (needed only after the vote)
+        const uint32_t B = ballot_bit(bs ^ Y0 ^ Y1 ^ Y2, bit);                // lanes whose three positions flip the parity
+        const uint32_t par = (uint32_t)__popc(B & lt) << k;                   // L (before the lane's first position) ^ L0, at bit k
+        // x = L ^ b at each position:  L_0 = par ^ L0,  L_1 = L_0 ^ g0,  L_2 = L_1 ^ g1
+        const uint32_t t0 = (par ^ L0 ^ b0) & bit;
+        const uint32_t t1 = (par ^ L0 ^ z0 ^ b1) & bit;
+        const uint32_t t2 = (par ^ L0 ^ z01 ^ b2) & bit;
         X0 |= t0; X1 |= t1; X2 |= t2;
         Y0 += t0 * 0xb3u; Y1 += t1 * 0xb3u; Y2 += t2 * 0xb3u;
     }
     // d = ((L ^ b) & 0xff) - L with L = X ^ b;  weight of position j is p^(n - j)
-    const uint32_t n = tb + 12u;
+    const uint32_t n = tb + 12u, j0 = 3u * (uint32_t)lane;
     unsigned long long s = 0;
-    if (vmask & 1u) s += (unsigned long long)(long long)((int)X0 - (int)(X0 ^ b0)) * tab.pw[n - lane];
-    if (vmask & 2u) s += (unsigned long long)(long long)((int)X1 - (int)(X1 ^ b1)) * tab.pw[n - 32 - lane];
-    if (vmask & 4u) s += (unsigned long long)(long long)((int)X2 - (int)(X2 ^ b2)) * tab.pw[n - 64 - lane];
-    // 64-bit sum over the warp as four 16-bit limbs (each limb sum < 2^21)
-    const uint32_t r0 = __reduce_add_sync(0xffffffffu, (uint32_t)s & 0xffffu), r1 = __reduce_add_sync(0xffffffffu, (uint32_t)(s >> 16) & 0xffffu);
-    const uint32_t r2 = __reduce_add_sync(0xffffffffu, (uint32_t)(s >> 32) & 0xffffu), r3 = __reduce_add_sync(0xffffffffu, (uint32_t)(s >> 48));
-    return tab.c0[n] + (unsigned long long)r0 + ((unsigned long long)r1 << 16) + ((unsigned long long)r2 << 32) + ((unsigned long long)r3 << 48);
+    if (vmask & 1u) s += (unsigned long long)(long long)((int)X0 - (int)(X0 ^ b0)) * tab.pw[n - j0];
+    if (vmask & 2u) s += (unsigned long long)(long long)((int)X1 - (int)(X1 ^ b1)) * tab.pw[n - j0 - 1];
+    if (vmask & 4u) s += (unsigned long long)(long long)((int)X2 - (int)(X2 ^ b2)) * tab.pw[n - j0 - 2];
+    // 64-bit sum over the warp as three limbs of 22 + 21 + 21 bits (each limb sum < 2^27)
+    const uint32_t r0 = __reduce_add_sync(0xffffffffu, (uint32_t)s & 0x3fffffu), r1 = __reduce_add_sync(0xffffffffu, (uint32_t)(s >> 22) & 0x1fffffu);
+    const uint32_t r2 = __reduce_add_sync(0xffffffffu, (uint32_t)(s >> 43));
+    return tab.c0[n] + (unsigned long long)r0 + ((unsigned long long)r1 << 22) + ((unsigned long long)r2 << 43);
 }
 
 // The chunk's token arrays as CBOR bytes: lane = block.  Row layout: tb token bytes, then 0xf6.
@@ -90,11 +110,16 @@ __device__ __forceinline__ void coop_layout_chunk(CoopSmem::Warp& W, const uint3
             const uint32_t tv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                // shortest-form CBOR uint, branch free: head byte, then the low len-1 bytes of t, big endian.  Five bytes are
+                // always stored; those past `len` are overwritten by the next token (or by the 0xf6 below).
                 const uint32_t t = tv[u];
-                if (t < 24u) { row[off] = (unsigned char)t; off += 1; }
-                else if (t < 256u) { row[off] = 0x18; row[off + 1] = (unsigned char)t; off += 2; }
-                else if (t < 65536u) { row[off] = 0x19; row[off + 1] = (unsigned char)(t >> 8); row[off + 2] = (unsigned char)t; off += 3; }
-                else { row[off] = 0x1a; row[off + 1] = (unsigned char)(t >> 24); row[off + 2] = (unsigned char)(t >> 16); row[off + 3] = (unsigned char)(t >> 8); row[off + 4] = (unsigned char)t; off += 5; }
+                const uint32_t len = t < 24u ? 1u : t < 256u ? 2u : t < 65536u ? 3u : 5u;
+                const uint32_t head = t < 24u ? t : t < 256u ? 0x18u : t < 65536u ? 0x19u : 0x1au;
+                const uint32_t be = t << (8u * (5u - len) & 31u);                  // the len-1 payload bytes, left aligned (len 1: unused)
+                row[off] = (unsigned char)head;
+                row[off + 1] = (unsigned char)(be >> 24); row[off + 2] = (unsigned char)(be >> 16);
+                row[off + 3] = (unsigned char)(be >> 8); row[off + 4] = (unsigned char)be;
+                off += len;
             }
         }
         row[off] = 0xf6;
@@ -102,15 +127,21 @@ __device__ __forceinline__ void coop_layout_chunk(CoopSmem::Warp& W, const uint3
     }
 }
 
-// this lane's parent-independent payload bytes of block blk (positions lane, lane+32, lane+64) and which of them exist
+// this lane's parent-independent payload bytes of block blk (positions 3*lane .. 3*lane+2) and which of them exist
 __device__ __forceinline__ void coop_block_bytes(const CoopSmem::Warp& W, int blk, int lane, uint32_t& tb, uint32_t& b0, uint32_t& b1, uint32_t& b2, uint32_t& vmask) {
     tb = W.tb[blk];
     const unsigned char* row = W.tokb[blk];
-    const int i0 = lane - 11, i1 = lane + 21, i2 = lane + 53;            // index into the row; row[tb] is the 0xf6
-    b0 = lane == 0 ? 0x83u : lane == 1 ? 0x1bu : lane == 10 ? 0x90u : (i0 >= 0 && (uint32_t)i0 <= tb) ? row[i0] : 0u;
-    b1 = (uint32_t)i1 <= tb ? row[i1] : 0u;
-    b2 = (uint32_t)i2 <= tb ? row[i2] : 0u;
-    vmask = ((lane <= 10 || (uint32_t)i0 <= tb) ? 1u : 0u) | ((uint32_t)i1 <= tb ? 2u : 0u) | ((uint32_t)i2 <= tb ? 4u : 0u);
+    const int i0 = 3 * lane - 11;                                        // index into the row of position 3*lane; row[tb] is the 0xf6
+    const bool v0 = lane <= 3 || (uint32_t)i0 <= tb, v1 = lane <= 2 || (uint32_t)(i0 + 1) <= tb, v2 = lane <= 2 || (uint32_t)(i0 + 2) <= tb;
+    uint32_t r0 = 0, r1 = 0, r2 = 0;
+    if (lane >= 4 && v0) r0 = row[i0];
+    if (lane >= 4 && v1) r1 = row[i0 + 1];
+    if (lane >= 3 && v2) r2 = row[i0 + 2];
+    // lane 0: 0x83, 0x1b, parent | lanes 1, 2: parent | lane 3: parent, 0x90, row[0]
+    b0 = lane == 0 ? 0x83u : lane >= 4 ? r0 : 0u;
+    b1 = lane == 0 ? 0x1bu : lane == 3 ? 0x90u : lane >= 4 ? r1 : 0u;
+    b2 = lane >= 3 ? r2 : 0u;
+    vmask = (v0 ? 1u : 0u) | (v1 ? 2u : 0u) | (v2 ? 4u : 0u);
 }
 
 // keys of a prompt's next nb (<= 32) blocks; lane j returns the key of block j (lanes >= nb: unspecified).  *last = key of

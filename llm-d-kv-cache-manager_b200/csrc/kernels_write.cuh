@@ -120,9 +120,12 @@ __global__ void get_request_key_kernel(TableView t, uint32_t model, uint64_t eng
 
 // ---- phase 1: request keys of a whole event batch ------------------------------------------------------------
 
-// Parents wanted by the batch: fingerprint(parent engine hash, pod, model) -> the latest block of the batch that carries
-// that engine hash for that pod, packed (sorted event index + 1) << 32 | block.  Open addressing, cleared per batch.
-struct WantEnt { unsigned long long fp, val; };
+// Parents wanted by the batch: fingerprint(parent engine hash, pod, model) -> the list of events that want it (their
+// consumers), chained through next[]; every block of the batch that carries a wanted hash offers itself to the consumers that
+// come AFTER it in the pod's queue, and each consumer keeps the latest such block: best[e] = (producer event + 1) << 32 | block.
+// That is the block whose Add is the last one before event e that touches the parent's engine key -- what GetRequestKey will
+// find when e is applied, unless a removal or another pod's worker gets in between (then phase 2 re-hashes the event).
+struct WantEnt { unsigned long long fp; unsigned int head; unsigned int pad; };
 
 __device__ __forceinline__ unsigned long long want_fp(uint64_t ehash, uint32_t podtier, uint32_t model) {
     const unsigned long long f = mix64(ehash ^ ((uint64_t)(podtier >> KVIDX_TIER_BITS) * 0xD6E8FEB86659FD93ull) ^ ((uint64_t)model << 48));
@@ -133,7 +136,8 @@ __device__ __forceinline__ bool event_hashable(const kvidx_event_t& e, uint32_t 
     return e.op == KVIDX_EV_BLOCK_STORED && e.n_hashes != 0 && e.n_tokens / B == e.n_hashes;
 }
 
-__global__ void want_parents_kernel(const kvidx_event_t* __restrict__ ev, int64_t n_ev, uint32_t B, WantEnt* map, uint32_t map_mask) {
+__global__ void want_parents_kernel(const kvidx_event_t* __restrict__ ev, int64_t n_ev, uint32_t B, WantEnt* map, uint32_t map_mask,
+                                    unsigned int* next) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= n_ev) return;
     const kvidx_event_t evt = ev[e];
@@ -141,12 +145,13 @@ __global__ void want_parents_kernel(const kvidx_event_t* __restrict__ ev, int64_
     const unsigned long long fp = want_fp(evt.parent_hash, evt.podtier, evt.model);
     for (uint32_t i = (uint32_t)fp & map_mask;; i = (i + 1) & map_mask) {
         const unsigned long long old = atomicCAS(&map[i].fp, 0ull, fp);
-        if (old == 0ull || old == fp) return;
+        if (old == 0ull || old == fp) { next[e] = atomicExch(&map[i].head, (unsigned int)e + 1u); return; }      // push front (0 = end of list)
     }
 }
-// lane per (event, 32-block group): offers its blocks to the map
+// lane per (event, 32-block group): offers its blocks to the later events that want them as a parent
 __global__ void offer_blocks_kernel(const kvidx_event_t* __restrict__ ev, int64_t n_ev, uint32_t B, const uint64_t* __restrict__ hashes,
-                                    WantEnt* map, uint32_t map_mask) {
+                                    const WantEnt* __restrict__ map, uint32_t map_mask, const unsigned int* __restrict__ next,
+                                    unsigned long long* best) {
     const int64_t e = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (e >= n_ev) return;
@@ -157,7 +162,11 @@ __global__ void offer_blocks_kernel(const kvidx_event_t* __restrict__ ev, int64_
         for (uint32_t i = (uint32_t)fp & map_mask;; i = (i + 1) & map_mask) {
             const unsigned long long cur = map[i].fp;
             if (cur == 0ull) break;                                       // nobody wants this block as a parent
-            if (cur == fp) { atomicMax(&map[i].val, ((unsigned long long)(e + 1) << 32) | b); break; }
+            if (cur == fp) {
+                for (unsigned int c = map[i].head; c != 0u; c = next[c - 1u])
+                    if ((long long)(c - 1u) > e) atomicMax(&best[c - 1u], ((unsigned long long)(e + 1) << 32) | b);
+                break;
+            }
         }
     }
 }
@@ -181,7 +190,7 @@ constexpr int kHashEvThreads = 128;
 //   ready[e]  0 not yet, 1 keys of event e are in keys[hash_off ..], 2 event has no keys
 __global__ void __launch_bounds__(kHashEvThreads)
 hash_events_kernel(const TableView t, const kvidx_event_t* __restrict__ ev, int64_t n_ev, const uint64_t* __restrict__ hashes,
-                   const uint32_t* __restrict__ tokens, const WantEnt* __restrict__ map, uint32_t map_mask,
+                   const uint32_t* __restrict__ tokens, const unsigned long long* __restrict__ best,
                    uint64_t* keys, uint64_t* pred, unsigned int* ready, unsigned long long* next) {
     const int lane = threadIdx.x & 31;
     const uint32_t B = t.block_size;
@@ -211,17 +220,9 @@ hash_events_kernel(const TableView t, const kvidx_event_t* __restrict__ ev, int6
                         tk = tokens + evt.tok_off;
                         h = t.init_hash; stage = 2;
                         if (evt.has_parent) {
-                            stage = 3;                                             // 3: resolve against the index as it is now
-                            const unsigned long long fp = want_fp(evt.parent_hash, evt.podtier, evt.model);
-                            for (uint32_t i = (uint32_t)fp & map_mask;; i = (i + 1) & map_mask) {
-                                const unsigned long long cur = map[i].fp;
-                                if (cur == 0ull) break;
-                                if (cur == fp) {
-                                    const unsigned long long v = map[i].val;
-                                    if (v != 0ull && (long long)(v >> 32) - 1 < idx) { pe = (long long)(v >> 32) - 1; pb = (uint32_t)v; stage = 1; }
-                                    break;
-                                }
-                            }
+                            const unsigned long long v = best[idx];                // latest earlier block of the batch carrying the parent hash
+                            if (v != 0ull) { pe = (long long)(v >> 32) - 1; pb = (uint32_t)v; stage = 1; }
+                            else stage = 3;                                        // 3: resolve against the index as it is now
                         }
                     }
                 }

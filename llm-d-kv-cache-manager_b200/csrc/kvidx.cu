@@ -141,6 +141,7 @@ struct kvidx {
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 / 3 = always the plain / class round pipeline,
                                    // 4 = always the warp-per-prompt cooperative kernel
     int64_t coop_max = 2048;       // batches up to this many prompts use the warp-per-prompt cooperative kernel
+    int64_t zerocopy_max = 32;     // host-buffer calls up to this many prompts skip the copy engine (tokens read from pinned host memory)
     int group_tma = 1;             // class pipeline: token chunks by TMA bulk copy (0: cp.async)
     struct SubmitQueue* queue = nullptr;   // coalesces concurrent host-buffer Score() callers (submit.cuh)
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
@@ -588,9 +589,66 @@ int score_host(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n,
     return rc;
 }
 
+// A handful of prompts (the size of one RPC, or of what the submission queue gathers at low load): no copy engine, no second
+// stream.  The cooperative kernel reads the tokens straight from PINNED HOST memory -- its TMA bulk copies fetch each 2 KB
+// chunk over PCIe one chunk ahead of the chain -- and writes the result rows straight back into pinned host memory; the call
+// is one launch and one stream synchronisation.  (cudaMallocHost memory is device-addressable under UVA.)
+int score_host_zerocopy(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
+                        const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys) {
+    const uint32_t P = x->tv.max_pods, FW = x->tv.filter_words;
+    const bool sparse = sp_cnt != nullptr;
+    const int64_t tb = tok_off[0], nt = tok_off[n] - tb;
+    const bool tok_pinned = nt == 0 || is_device_accessible_host(tok);
+    const size_t a8 = 63;
+    const size_t in_bytes = (((size_t)(n + 1) * 8 + a8) & ~a8) + (model ? (((size_t)n * 4 + a8) & ~a8) : 0) + (filter ? (((size_t)n * FW * 8 + a8) & ~a8) : 0) +
+                            (tok_pinned ? 0 : (size_t)nt * 4 + 64);
+    CK(x->h_stage[0].need(in_bytes + 64));
+    uint8_t* hs = x->h_stage[0].as<uint8_t>();
+    size_t o = 0;
+    int64_t* h_off = reinterpret_cast<int64_t*>(hs); memcpy(h_off, tok_off, (size_t)(n + 1) * 8); o += ((size_t)(n + 1) * 8 + a8) & ~a8;
+    const uint32_t* h_model = nullptr; const uint64_t* h_filter = nullptr;
+    if (model) { memcpy(hs + o, model, (size_t)n * 4); h_model = reinterpret_cast<const uint32_t*>(hs + o); o += ((size_t)n * 4 + a8) & ~a8; }
+    if (filter) { memcpy(hs + o, filter, (size_t)n * FW * 8); h_filter = reinterpret_cast<const uint64_t*>(hs + o); o += ((size_t)n * FW * 8 + a8) & ~a8; }
+    const uint32_t* h_tok = tok ? tok + tb : nullptr;                     // token of absolute index tb
+    if (!tok_pinned) { memcpy(hs + o, tok + tb, (size_t)nt * 4); h_tok = reinterpret_cast<const uint32_t*>(hs + o); }
+    // results: straight into the caller's buffers when those are pinned, else through the pinned staging
+    const bool out_direct = sparse ? (is_device_accessible_host(sp_pods) && is_device_accessible_host(sp_scores) && is_device_accessible_host(sp_cnt) &&
+                                      (!has_keys || is_device_accessible_host(has_keys)))
+                                   : (is_device_accessible_host(dense) && (!has_keys || is_device_accessible_host(has_keys)));
+    ScoreArgs a{h_tok, h_off, tb, n, h_model, model0, h_filter, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint8_t* ho = nullptr;
+    if (out_direct) { a.dense = dense; a.sp_pods = sp_pods; a.sp_scores = sp_scores; a.sp_cnt = sp_cnt; a.has_keys = has_keys; }
+    else {
+        const size_t out_bytes = sparse ? (size_t)n * (kMaxEnt * 10 + 2) : (size_t)n * (P * 8 + 1);
+        CK(x->h_out[0].need(out_bytes + 64));
+        ho = x->h_out[0].as<uint8_t>();
+        if (!sparse) { a.dense = reinterpret_cast<double*>(ho); a.has_keys = ho + (size_t)n * P * 8; }
+        else { a.sp_scores = reinterpret_cast<double*>(ho); a.sp_pods = reinterpret_cast<uint16_t*>(ho + (size_t)n * kMaxEnt * 8); a.sp_cnt = ho + (size_t)n * kMaxEnt * 10; a.has_keys = a.sp_cnt + n; }
+    }
+    if (int rc = check_shards(x)) return rc;
+    CK(cudaStreamWaitEvent(x->stream, x->ev_write, 0));
+    const int64_t ctas = std::min<int64_t>((n + kCoopWarps - 1) / kCoopWarps, (int64_t)x->sm_count * 4);
+    coop_score_kernel<16><<<(unsigned)ctas, kCoopThreads, sizeof(CoopSmem), x->stream>>>(x->tv, a);
+    x->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(x->stream));
+    if (!out_direct) {
+        if (!sparse) { memcpy(dense, ho, (size_t)n * P * 8); if (has_keys) memcpy(has_keys, ho + (size_t)n * P * 8, (size_t)n); }
+        else {
+            memcpy(sp_scores, ho, (size_t)n * kMaxEnt * 8); memcpy(sp_pods, ho + (size_t)n * kMaxEnt * 8, (size_t)n * kMaxEnt * 2);
+            memcpy(sp_cnt, ho + (size_t)n * kMaxEnt * 10, (size_t)n);
+            if (has_keys) memcpy(has_keys, ho + (size_t)n * kMaxEnt * 10 + n, (size_t)n);
+        }
+    }
+    return 0;
+}
+
 int score_host_locked(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t n, const uint32_t* model, uint32_t model0,
                       const uint64_t* filter, double* dense, uint16_t* sp_pods, double* sp_scores, uint8_t* sp_cnt, uint8_t* has_keys) {
     int rc = 0;
+    if (n <= x->zerocopy_max && x->tv.block_size == 16 && !x->tv.req_stamp && x->score_kernel != 1 && (x->score_path == 0 || x->score_path == 4) &&
+        tok_off[n] - tok_off[0] <= (4ll << 20))
+        return score_host_zerocopy(x, tok, tok_off, n, model, model0, filter, dense, sp_pods, sp_scores, sp_cnt, has_keys);
     const uint32_t P = x->tv.max_pods, FW = x->tv.filter_words;
     const bool sparse = sp_cnt != nullptr;
     const size_t out_row = sparse ? (size_t)kMaxEnt * (sizeof(double) + sizeof(uint16_t)) + 2 : (size_t)P * sizeof(double) + 1;
@@ -962,6 +1020,7 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
     if (const char* k = getenv("KVIDX_SCORE_KERNEL")) x->score_kernel = (k[0] == 'v' ? atoi(k + 1) : atoi(k)) == 1 ? 1 : 2;
     if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : !strcmp(k, "classes") ? 3 : !strcmp(k, "coop") ? 4 : 0;
     if (const char* k = getenv("KVIDX_COOP_MAX")) x->coop_max = atoll(k);
+    if (const char* k = getenv("KVIDX_ZEROCOPY_MAX")) x->zerocopy_max = atoll(k);
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
     if (const char* k = getenv("KVIDX_CLASSES_MIN")) x->classes_min = atoll(k);
     if (const char* k = getenv("KVIDX_CLASSES_SHARING")) x->classes_min_sharing = atof(k);
@@ -1343,17 +1402,23 @@ int launch_apply_events(kvidx* x, const kvidx_event_t* d_ev_sorted, const int64_
         const uint64_t map_slots = pow2ceil((uint64_t)std::max<int64_t>(2 * n_events, 64));
         CK(x->d_wkeys.need((size_t)n_hashes * 8));
         CK(x->d_wpred.need((size_t)n_events * 8));
-        CK(x->d_wready.need((size_t)n_events * 4 + 16));
+        // one zeroed block: work counter (16 B) | ready[n] | next[n] | best[n] (8-byte aligned)
+        const size_t n4 = ((size_t)n_events + 3) & ~(size_t)3;
+        const size_t zbytes = 16 + n4 * 4 + n4 * 4 + (size_t)n_events * 8;
+        CK(x->d_wready.need(zbytes));
         CK(x->d_wmap.need((size_t)map_slots * sizeof(WantEnt)));
-        unsigned int* d_ready = x->d_wready.as<unsigned int>() + 4;
-        unsigned long long* d_next = x->d_wready.as<unsigned long long>();
-        CK(cudaMemsetAsync(x->d_wready.p, 0, (size_t)n_events * 4 + 16, st));
+        uint8_t* zb = x->d_wready.as<uint8_t>();
+        unsigned long long* d_next = reinterpret_cast<unsigned long long*>(zb);
+        unsigned int* d_ready = reinterpret_cast<unsigned int*>(zb + 16);
+        unsigned int* d_chain = reinterpret_cast<unsigned int*>(zb + 16 + n4 * 4);
+        unsigned long long* d_best = reinterpret_cast<unsigned long long*>(zb + 16 + n4 * 8);
+        CK(cudaMemsetAsync(zb, 0, zbytes, st));
         CK(cudaMemsetAsync(x->d_wmap.p, 0, (size_t)map_slots * sizeof(WantEnt), st));
         const int T = 256;
-        want_parents_kernel<<<(unsigned)((n_events + T - 1) / T), T, 0, st>>>(d_ev_sorted, n_events, x->tv.block_size, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1));
-        offer_blocks_kernel<<<(unsigned)((n_events * 32 + T - 1) / T), T, 0, st>>>(d_ev_sorted, n_events, x->tv.block_size, d_hashes, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1));
+        want_parents_kernel<<<(unsigned)((n_events + T - 1) / T), T, 0, st>>>(d_ev_sorted, n_events, x->tv.block_size, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1), d_chain);
+        offer_blocks_kernel<<<(unsigned)((n_events * 32 + T - 1) / T), T, 0, st>>>(d_ev_sorted, n_events, x->tv.block_size, d_hashes, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1), d_chain, d_best);
         const int64_t ctas = std::min<int64_t>((n_events + kHashEvThreads - 1) / kHashEvThreads, (int64_t)x->sm_count * 8);
-        hash_events_kernel<<<(unsigned)ctas, kHashEvThreads, 0, st>>>(x->tv, d_ev_sorted, n_events, d_hashes, d_tokens, x->d_wmap.as<WantEnt>(), (uint32_t)(map_slots - 1),
+        hash_events_kernel<<<(unsigned)ctas, kHashEvThreads, 0, st>>>(x->tv, d_ev_sorted, n_events, d_hashes, d_tokens, d_best,
                                                                      x->d_wkeys.as<uint64_t>(), x->d_wpred.as<uint64_t>(), d_ready, d_next);
         x->launches += 3;
         CK(cudaGetLastError());

@@ -309,6 +309,7 @@ def _select_path(monkeypatch, path):
         return
     if path == "auto":                       # the library chooses: here every batch is "large", so it is the class pipeline
         monkeypatch.setenv("KVIDX_ROUNDS_MIN", "1")        # or the per-prompt rounds, by how much the batch repeats itself
+        monkeypatch.setenv("KVIDX_COOP_MAX", "0")          # (small batches would otherwise take the warp-per-prompt kernel)
         monkeypatch.setenv("KVIDX_CLASSES_MIN", "64")
         monkeypatch.setenv("KVIDX_ROUNDS_OVERLAP_MIN", "64")
         return
