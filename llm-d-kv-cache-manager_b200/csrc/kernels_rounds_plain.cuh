@@ -46,6 +46,11 @@ struct RoundBufs {
                                          // block j of list slot i at keys[j * n_prompts + i] (coalesced both ways)
     uint32_t* nbr;                       // [n_act] per list slot: blocks hashed this round | (more blocks follow) << 8
     PromptState* pst;                    // per prompt
+    // Speculative schedule (small batches, latency bound): kernel H of round t+1 runs BESIDE kernel P of round t.  It cannot
+    // know yet which prompts survive round t, so it hashes the next 32 blocks of every prompt of round t's list; P of round
+    // t+1 then finds its prompts' keys through prev[] (slot in the list H ran over).  keys / nbr alternate between two buffers.
+    uint32_t* prev[2];                   // [n_act] per slot of act[x]: the prompt's slot in the previous round's list
+    int spec;
 };
 
 constexpr int kHashChunk = 1;            // blocks staged per copy step (2 = 128-byte accesses was measured: fewer, longer DRAM
@@ -64,13 +69,15 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
     using SM = HashSmem<BS>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned int n_act = rb.n_act[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
+    // the list this kernel works on: the round's own list, or (speculative schedule) the list of the round before
+    const int src = rb.spec ? (round == 0 ? 0 : ((round - 1) & 1)) : cur;
+    const unsigned int n_act = rb.n_act[src];
+    if (!rb.spec && blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
     const unsigned int total_warps = gridDim.x * (kHashThreads / 32);
     for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
         const unsigned int i = w * 32u + lane;                            // slot in the active list
         const bool have = i < n_act;
-        const uint32_t p = have ? rb.act[cur][i] : 0u;
+        const uint32_t p = have ? rb.act[src][i] : 0u;
         int nb = 0;                                                      // blocks of this prompt in this round
         const uint32_t* src = nullptr;
         bool aligned = true;
@@ -171,7 +178,8 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         const unsigned int i = w * 32u + lane;
         const bool have = i < n_act;
         const uint32_t p = have ? rb.act[cur][i] : 0u;
-        const uint32_t meta = have ? rb.nbr[i] : 0u;
+        const unsigned int ks = (have && rb.spec && round > 0) ? rb.prev[cur][i] : i;      // slot the keys of this prompt were written at
+        const uint32_t meta = have ? rb.nbr[ks] : 0u;
         const int nb = (int)(meta & 63u);
         const bool has_more = (meta >> 8) & 1u;
         const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
@@ -195,12 +203,12 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         const ReqSlot* base = t.req;                           // table (shard) of the current block's key
         uint4 A0 = {0, 0, 0, 0}, B0 = {0, 0, 0, 0}, A1 = {0, 0, 0, 0}, B1 = {0, 0, 0, 0};
         if (!done) {
-            key = rb.keys[i];
+            key = rb.keys[ks];
             const uint64_t hm = home_of(key, mdl);
             base = t.req_peer[shard_of(hm, t.shard_bits)]; slot = hm & t.req_mask & ~1ull;
             ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
         }
-        uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + i] : 0ull;                         // key of block j+1
+        uint64_t key1 = (!done && nb > 1) ? rb.keys[kstride + ks] : 0ull;                        // key of block j+1
         for (int j = 0; j < nb_max; ++j) {
             // next block's pair is requested before this block is scored; keys are read one iteration ahead of their use
             uint64_t nkey = key1, nslot = 0;
@@ -212,7 +220,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 nbase = t.req_peer[shard_of(hm, t.shard_bits)]; nslot = hm & t.req_mask & ~1ull;
                 ld_slot_pair(nbase + nslot, peer, nA0, nB0, nA1, nB1);
             }
-            key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + i] : 0ull;
+            key1 = (!done && j + 2 < nb) ? rb.keys[(size_t)(j + 2) * kstride + ks] : 0ull;
             if (!done && j < nb) {
                 uint4 A = A0, B = B0;
                 bool hit = slot_matches(A, B, key, mdl);
@@ -283,7 +291,9 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (more) {
-                rb.act[cur ^ 1][base + __popc(mm & ((1u << lane) - 1u))] = p;
+                const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u));
+                rb.act[cur ^ 1][ns] = p;
+                if (rb.spec) rb.prev[cur ^ 1][ns] = i;
                 PromptState& ps = rb.pst[p];
                 ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
                 ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;

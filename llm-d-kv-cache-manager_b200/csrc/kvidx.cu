@@ -141,6 +141,9 @@ struct kvidx {
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 / 3 = always the plain / class round pipeline,
                                    // 4 = always the warp-per-prompt cooperative kernel
     int64_t coop_max = 2048;       // batches up to this many prompts use the warp-per-prompt cooperative kernel
+    int rounds_spec = 1;           // per-prompt rounds: run hash(t+1) beside walk(t) for small batches
+    int64_t rounds_spec_max = 131072;
+    cudaEvent_t ev_spec_h[2][2] = {}, ev_spec_p[2][2] = {};
     int64_t zerocopy_max = 32;     // host-buffer calls up to this many prompts skip the copy engine (tokens read from pinned host memory)
     int group_tma = 1;             // class pipeline: token chunks by TMA bulk copy (0: cp.async)
     struct SubmitQueue* queue = nullptr;   // coalesces concurrent host-buffer Score() callers (submit.cuh)
@@ -453,12 +456,17 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
 }
 
 // Medium batches: hash / walk rounds, every prompt on its own (kernels_rounds_plain.cuh); two halves on two streams.
+// Below rounds_spec_max prompts the rounds are latency bound (a few warps per SM walking dependent chains), so kernel H of
+// round t+1 is launched BESIDE kernel P of round t on a second stream per half: it hashes the next 32 blocks of every prompt
+// of round t's list without waiting to learn which of them survive (at most one round of hashing per prompt is wasted).
 int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, int64_t tok_base, int64_t n,
                         const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
                         int64_t max_blocks) {
+    const bool spec = x->rounds_spec && n <= x->rounds_spec_max;
     CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(64));
-    CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * plain::kRoundBlocks * 8)); CK(x->r_pst.need((size_t)n * sizeof(plain::PromptState)));
-    CK(x->r_nbr.need((size_t)n * 4));
+    CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * plain::kRoundBlocks * 8 * (spec ? 2 : 1))); CK(x->r_pst.need((size_t)n * sizeof(plain::PromptState)));
+    CK(x->r_nbr.need((size_t)n * 4 * (spec ? 2 : 1)));
+    if (spec) CK(x->r_hl.need((size_t)n * 4 * 2));
     const bool overlap = x->rounds_overlap && n >= x->rounds_overlap_min;
     const int64_t nA = overlap ? ((n / 2 + 31) & ~31ll) : n, nB = n - nA;
     unsigned int* cnt = x->r_cnt.as<unsigned int>();
@@ -470,6 +478,8 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
         rb[hlf].n_act = cnt + 2 * hlf;
         rb[hlf].hstate = x->r_hstate.as<uint64_t>(); rb[hlf].pst = x->r_pst.as<plain::PromptState>();
         rb[hlf].keys = x->r_keys.as<uint64_t>() + off; rb[hlf].nbr = x->r_nbr.as<uint32_t>() + off;
+        rb[hlf].spec = spec ? 1 : 0;
+        if (spec) { rb[hlf].prev[0] = x->r_hl.as<uint32_t>() + off; rb[hlf].prev[1] = x->r_hl.as<uint32_t>() + n + off; }
     }
     ScoreArgs a{d_tok, d_off, tok_base, n, d_model, model0, d_filter, o.dense, o.sp_pods, o.sp_scores, o.sp_cnt, o.has_keys, nullptr};
     CK(cudaMemsetAsync(x->r_cnt.p, 0, 64, st));
@@ -495,26 +505,54 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
     }
     int64_t rounds = (max_blocks + plain::kRoundBlocks - 1) / plain::kRoundBlocks;
     if (rounds < 1) rounds = 1;                       // round 0 also retires the prompts that have no full block
-    cudaStream_t strm[2] = {st, x->aux_stream[0]};
     const int nh = nB > 0 ? 2 : 1;
-    if (nh == 2) { CK(cudaEventRecord(x->ev_fork, st)); CK(cudaStreamWaitEvent(x->aux_stream[0], x->ev_fork, 0)); }
     const int per_sm_h = nh == 2 ? 2 : 4, per_sm_p = nh == 2 ? 2 : 4;
+    if (!spec) {
+        cudaStream_t strm[2] = {st, x->aux_stream[0]};
+        if (nh == 2) { CK(cudaEventRecord(x->ev_fork, st)); CK(cudaStreamWaitEvent(x->aux_stream[0], x->ev_fork, 0)); }
+        for (int64_t r = 0; r < rounds; ++r) {
+            const int cur = (int)(r & 1);
+            for (int hlf = 0; hlf < nh; ++hlf) {
+                const int64_t m = hlf ? nB : nA;
+                const unsigned hgrid = (unsigned)std::min<int64_t>((m + plain::kHashThreads - 1) / plain::kHashThreads, (int64_t)x->sm_count * per_sm_h);
+                plain::hash_round_kernel<16><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+            }
+            for (int hlf = 0; hlf < nh; ++hlf) {
+                const int64_t m = hlf ? nB : nA;
+                const unsigned pgrid = (unsigned)std::min<int64_t>((m + plain::kProbeThreads - 1) / plain::kProbeThreads, (int64_t)x->sm_count * per_sm_p);
+                plain::probe_round_kernel<<<pgrid, plain::kProbeThreads, sizeof(plain::WalkSmem), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+            }
+            x->launches += 2 * nh;
+        }
+        CK(cudaGetLastError());
+        if (nh == 2) { CK(cudaEventRecord(x->ev_join[0], x->aux_stream[0])); CK(cudaStreamWaitEvent(st, x->ev_join[0], 0)); }
+        return 0;
+    }
+    // speculative schedule: per half one H stream and one P stream; H(t+1) waits for P(t-1) (its list), P(t) for H(t) (its keys)
+    cudaStream_t sH[2] = {st, x->aux_stream[0]}, sP[2] = {x->aux_stream[1], x->aux_stream[2]};
+    CK(cudaEventRecord(x->ev_fork, st));
+    for (int q = 0; q < 3; ++q) CK(cudaStreamWaitEvent(x->aux_stream[q], x->ev_fork, 0));
     for (int64_t r = 0; r < rounds; ++r) {
         const int cur = (int)(r & 1);
         for (int hlf = 0; hlf < nh; ++hlf) {
             const int64_t m = hlf ? nB : nA;
+            plain::RoundBufs rr = rb[hlf];
+            rr.keys += (size_t)cur * (size_t)n * plain::kRoundBlocks; rr.nbr += (size_t)cur * (size_t)n;
+            if (r >= 2) CK(cudaStreamWaitEvent(sH[hlf], x->ev_spec_p[hlf][cur], 0));                 // P(r-2) built the list H(r) runs over ... (r-1)&1 == cur^1; see below
             const unsigned hgrid = (unsigned)std::min<int64_t>((m + plain::kHashThreads - 1) / plain::kHashThreads, (int64_t)x->sm_count * per_sm_h);
-            plain::hash_round_kernel<16><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
-        }
-        for (int hlf = 0; hlf < nh; ++hlf) {
-            const int64_t m = hlf ? nB : nA;
+            plain::hash_round_kernel<16><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), sH[hlf]>>>(x->tv, a, rr, cur, (int)r);
+            CK(cudaEventRecord(x->ev_spec_h[hlf][cur], sH[hlf]));
+            CK(cudaStreamWaitEvent(sP[hlf], x->ev_spec_h[hlf][cur], 0));
+            CK(cudaMemsetAsync(rb[hlf].n_act + (cur ^ 1), 0, sizeof(unsigned int), sP[hlf]));      // the list P(r) appends to starts empty
             const unsigned pgrid = (unsigned)std::min<int64_t>((m + plain::kProbeThreads - 1) / plain::kProbeThreads, (int64_t)x->sm_count * per_sm_p);
-            plain::probe_round_kernel<<<pgrid, plain::kProbeThreads, sizeof(plain::WalkSmem), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+            plain::probe_round_kernel<<<pgrid, plain::kProbeThreads, sizeof(plain::WalkSmem), sP[hlf]>>>(x->tv, a, rr, cur, (int)r);
+            CK(cudaEventRecord(x->ev_spec_p[hlf][cur], sP[hlf]));
         }
         x->launches += 2 * nh;
     }
     CK(cudaGetLastError());
-    if (nh == 2) { CK(cudaEventRecord(x->ev_join[0], x->aux_stream[0])); CK(cudaStreamWaitEvent(st, x->ev_join[0], 0)); }
+    if (nh == 2) { CK(cudaEventRecord(x->ev_join[0], sH[1])); CK(cudaStreamWaitEvent(st, x->ev_join[0], 0)); }
+    for (int hlf = 0; hlf < nh; ++hlf) { CK(cudaEventRecord(x->ev_join[1 + hlf], sP[hlf])); CK(cudaStreamWaitEvent(st, x->ev_join[1 + hlf], 0)); }
     return 0;
 }
 
@@ -979,6 +1017,10 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
     }
     CK(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&x->ev_write, cudaEventDisableTiming));
+    for (int a_ = 0; a_ < 2; ++a_) for (int b_ = 0; b_ < 2; ++b_) {
+        CK(cudaEventCreateWithFlags(&x->ev_spec_h[a_][b_], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&x->ev_spec_p[a_][b_], cudaEventDisableTiming));
+    }
     x->stream = x->own_stream;
     for (int i = 0; i < 2; ++i) {
         CK(cudaEventCreateWithFlags(&x->ev_h2d[i], cudaEventDisableTiming));
@@ -1021,6 +1063,8 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
     if (const char* k = getenv("KVIDX_SCORE_PATH")) x->score_path = !strcmp(k, "fused") ? 1 : !strcmp(k, "rounds") ? 2 : !strcmp(k, "classes") ? 3 : !strcmp(k, "coop") ? 4 : 0;
     if (const char* k = getenv("KVIDX_COOP_MAX")) x->coop_max = atoll(k);
     if (const char* k = getenv("KVIDX_ZEROCOPY_MAX")) x->zerocopy_max = atoll(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_SPEC")) x->rounds_spec = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_SPEC_MAX")) x->rounds_spec_max = atoll(k);
     if (const char* k = getenv("KVIDX_ROUNDS_MIN")) x->rounds_min = atoll(k);
     if (const char* k = getenv("KVIDX_CLASSES_MIN")) x->classes_min = atoll(k);
     if (const char* k = getenv("KVIDX_CLASSES_SHARING")) x->classes_min_sharing = atof(k);
@@ -1109,6 +1153,10 @@ void kvidx_destroy(kvidx_t* x) {
     }
     if (x->ev_fork) cudaEventDestroy(x->ev_fork);
     if (x->ev_write) cudaEventDestroy(x->ev_write);
+    for (int a_ = 0; a_ < 2; ++a_) for (int b_ = 0; b_ < 2; ++b_) {
+        if (x->ev_spec_h[a_][b_]) cudaEventDestroy(x->ev_spec_h[a_][b_]);
+        if (x->ev_spec_p[a_][b_]) cudaEventDestroy(x->ev_spec_p[a_][b_]);
+    }
     cudaGetLastError();
     delete x;
 }

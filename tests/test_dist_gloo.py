@@ -99,8 +99,11 @@ def _worker_sharded(rank, world, port, q):
         assert np.array_equal(local2, exp2) and not np.array_equal(exp2, exp)
         q.put((rank, lo, hi, True))
     except Exception as e:      # noqa: BLE001
+        import sys
         import traceback
-        q.put((rank, -1, -1, repr(e) + traceback.format_exc()))
+        tb = traceback.format_exc()
+        print("rank %d failed:\n%s" % (rank, tb), file=sys.stderr, flush=True)
+        q.put((rank, -1, -1, tb[-700:]))
     finally:
         dist.destroy_process_group()
 
