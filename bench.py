@@ -235,7 +235,8 @@ def run_reference(args):
                             "sample": "%d steps x %d prompts, one GetPodScores per call on %d threads (best of a 1..%d sweep; C++ restatement "
                                       "of the Go path; Go toolchain absent); index fill %.1fs" % (len(times), sample, threads, host_threads(), fill_s),
                             "host_cores": host_threads(),
-                            "p99_latency_ms": float(np.percentile(lat, 99)) / 1e6, "p50_latency_ms": float(np.percentile(lat, 50)) / 1e6},
+                            "p99_latency_ms": float(np.percentile(lat, 99)) / 1e6, "p50_latency_ms": float(np.percentile(lat, 50)) / 1e6,
+                            "go_probe": go_probe()},
            "e2e": {"value": value, "unit": "prompts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)
@@ -629,6 +630,22 @@ def run_ours(args):
         lat["batch_%d" % nb] = {"p50_ms": float(np.percentile(ts, 50)), "p99_ms": float(np.percentile(ts, 99))}
     lat["batch_1_matched_blocks"] = int(e_m[0])
 
+    # ---- 1000 concurrent single-prompt callers (the load shape of the reference's gRPC server: one goroutine per RPC, no
+    # batching anywhere, server.go:70-96) through the C ABI from a plain C++ load generator; the library's submission queue
+    # turns them into shared launches.  Every returned score is verified inside the generator. ----
+    clients = None
+    qps_bin = os.path.join(PKG, "lib", "kvidx_qps")
+    if rank == 0 and world == 1 and os.path.exists(qps_bin) and not os.environ.get("KVIDX_BENCH_SKIP_QPS"):
+        clients = {}
+        for nthreads in (1, 64, 1000):
+            try:
+                r = subprocess.run([qps_bin, str(nthreads), "2.0", "4096", str(wl.T)], capture_output=True, text=True, timeout=300)
+                clients["threads_%d" % nthreads] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+            except Exception as e:      # noqa: BLE001
+                clients["threads_%d" % nthreads] = {"error": repr(e)[:300]}
+        clients["note"] = ("kvidx_qps: N OS threads, one %d-token prompt per kvidx_score_batch_sparse call, 1 M-block index; calls/s and call latency; "
+                           "wrong_results must be 0" % wl.T)
+
     # ---- CPU baseline (rank 0, N=1 only): the reference-path port on the host cores ----
     cpu = None
     if rank == 0 and world == 1 and not os.environ.get("KVIDX_BENCH_SKIP_CPU"):
@@ -712,7 +729,7 @@ def run_ours(args):
                                       "host sort + H2D + hash_events_kernel + apply_events_kernel, per rank; A_ev = 136 B per block (SURVEY 8(d)); "
                                       "this rank's share of the index = %d keys" % (wl.bpe, fill["keys"])},
                "p99_step_ms": float(np.percentile(step_ms, 99)), "latency": lat, "value_at_64k_batch": value_64k, "value_at_512k_batch": value_512k,
-               "mixed_read_write": mixed, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense": e2e_dense,
+               "mixed_read_write": mixed, "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "e2e_dense": e2e_dense, "concurrent_clients": clients,
                "gpu_launches": int(launches), "clocks": clocks}
         if "replicas" in res and primary != "replicas":
             out["value_replicas"] = res["replicas"]["value"]

@@ -145,7 +145,7 @@ struct kvidx {
     int64_t rounds_spec_max = 131072;
     cudaEvent_t ev_spec_h[2][2] = {}, ev_spec_p[2][2] = {};
     int64_t zerocopy_max = 32;     // host-buffer calls up to this many prompts skip the copy engine (tokens read from pinned host memory)
-    int group_tma = 1;             // class pipeline: token chunks by TMA bulk copy (0: cp.async)
+    int group_tma = 0;             // class pipeline: token chunks by TMA bulk copy instead of cp.async (measured: 2 % slower per step)
     struct SubmitQueue* queue = nullptr;   // coalesces concurrent host-buffer Score() callers (submit.cuh)
     int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
     int64_t classes_min = 393216;  // ... and at least this large, the prefix-class round pipeline

@@ -328,10 +328,14 @@ def _select_path(monkeypatch, path):
         monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "0")
     elif var == "whole":
         monkeypatch.setenv("KVIDX_ROUNDS_DEDUP", "1")
+    elif var == "tma":                       # token chunks of the class pipeline by TMA bulk copy instead of cp.async
+        monkeypatch.setenv("KVIDX_GROUP_TMA", "1")
+    elif var == "nospec":                    # per-prompt rounds without the speculative hash / walk overlap
+        monkeypatch.setenv("KVIDX_ROUNDS_SPEC", "0")
 
 
-ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "classes", "classes2", "classes8", "classes-nosort", "classes-nodedup", "classes-whole",
-               "classes4-whole", "auto"]
+ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "rounds-nospec", "rounds2-nospec", "classes", "classes2", "classes8", "classes-nosort",
+               "classes-nodedup", "classes-whole", "classes4-whole", "classes-tma", "classes8-tma", "auto"]
 PATHS = ["v1", "fused", "coop"] + ROUND_PATHS
 
 
