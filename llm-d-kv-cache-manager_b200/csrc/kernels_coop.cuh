@@ -18,7 +18,7 @@
 //     (a 16-token block is 28..92 CBOR bytes);
 //   * every block's payload starts from the FNV offset basis (the parent hash enters as BYTES), so h_0 * p^n is a table.
 //
-//   A block then costs ~8 ballot/popcount rounds plus one warp reduction instead of ~90 dependent multiply steps.
+//   A block then costs 8 ballot/popcount rounds plus one warp reduction instead of ~90 dependent multiply steps.
 //   The token bytes of a whole 32-block chunk are laid out in shared memory beforehand (lane = block, off the chain's
 //   critical path); only the 8 parent bytes of a payload wait for the previous key.
 //
@@ -44,15 +44,16 @@ struct CoopSmem {
         uint32_t tok[2][kRoundBlocks * 16];                             // two 2 KB chunks (TMA destinations)
         unsigned char tokb[kRoundBlocks][kCoopRow];                     // CBOR bytes of the chunk's token arrays
         uint32_t tb[kRoundBlocks];                                      // bytes per block
+        uint32_t lanew[kRoundBlocks][33];                               // per block, per lane: its three payload bytes | vmask << 24
+                                                                        // (rows padded to 33 words: conflict free both ways)
         unsigned long long bar[2];                                      // mbarriers of the two chunk buffers
     } w[kCoopWarps];
 };
 
-// ballot of "g ^ (par & e) is non-zero" (one LOP3 with predicate output + VOTE): g and e are 0 / 1
-__device__ __forceinline__ uint32_t ballot_sel(uint32_t g, uint32_t par, uint32_t e) {
+// ballot of "bit `bit` of z is set" (one LOP3 with predicate output + VOTE)
+__device__ __forceinline__ uint32_t ballot_bit(uint32_t z, uint32_t bit) {
     uint32_t r;
-    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %2, %3;\n\txor.b32 t, t, %1;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}"
-                 : "=r"(r) : "r"(g), "r"(par), "r"(e));
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(r) : "r"(z), "r"(bit));
     return r;
 }
 
@@ -60,12 +61,13 @@ __device__ __forceinline__ uint32_t ballot_sel(uint32_t g, uint32_t par, uint32_
 // 0x90, tb token bytes, 0xf6: n = tb + 12 bytes.  Lane l owns the three CONSECUTIVE positions 3l, 3l+1, 3l+2 (b0..b2: the
 // bytes there as far as they do not depend on the parent -- 0 past the payload; vmask bit i: position 3l+i is inside it).
 //
-// Bit plane j of the 8-bit recurrence L' = ((L ^ b) * 0xb3) & 0xff: every position contributes g = bit j of (b ^ Y), Y the
-// carry word (x mod 2^j) * 0xb3; L_j before a lane's first position is the XOR of all g of earlier lanes -- ONE ballot of
+// Bit plane k of the 8-bit recurrence L' = ((L ^ b) * 0xb3) & 0xff: every position contributes g = bit k of (b ^ Y), Y the
+// carry word (x mod 2^k) * 0xb3; L_k before a lane's first position is the XOR of all g of earlier lanes -- ONE ballot of
 // the lanes' parities and a popcount -- and inside the lane two more register XORs.  The planes are inherently sequential
-// (plane j+1's carries need plane j's x bits), so what matters is the length of ballot -> popcount -> next ballot: the next
-// plane's lane parity is prepared for BOTH values of this plane's prefix parity while the ballot is in flight (x = par ^ c, so
-// the carry word is Y or Y + (0xb3 << j)), and choosing between them is one LOP3 with predicate output feeding the next VOTE.
+// (plane k+1's carries need plane k's x bits): a block is eight rounds of VOTE -> POPC -> (4 ALU) -> VOTE.  Measured
+// (scripts/ubench_coop2.cu, one warp): ~130 cycles per plane, of which the VOTE + POPC pair is the larger part -- preparing
+// the next plane's parity for both outcomes while the ballot is in flight (a single LOP3.P between POPC and the next VOTE)
+// changed nothing (1337 vs 1280 cycles per block), and a shuffle XOR scan instead of the ballot doubles it.
 __device__ __forceinline__ uint64_t coop_hash_block(const CoopTables& tab, uint64_t parent, uint32_t tb, uint32_t b0, uint32_t b1, uint32_t b2,
                                                     uint32_t vmask, int lane, uint32_t lt) {
     if (lane < 4) {                                         // positions 2..9 carry the parent, most significant byte first
@@ -77,23 +79,20 @@ __device__ __forceinline__ uint64_t coop_hash_block(const CoopTables& tab, uint6
     }
     constexpr uint32_t L0 = (uint32_t)(kFnvOffset & 0xffu);
     const uint32_t bs = b0 ^ b1 ^ b2;
+    // Y_i = (x_i mod 2^k) * 0xb3: its bit k is the carry into plane k;  X_i accumulates x_i = L_i ^ b_i
     uint32_t X0 = 0, X1 = 0, X2 = 0, Y0 = 0, Y1 = 0, Y2 = 0;
-    uint32_t B = __ballot_sync(0xffffffffu, (bs & 1u) != 0u);                  // plane 0: no carries yet
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        // --- in the shadow of the ballot: this plane's c_i (x_i = par ^ c_i) and the next plane's parity for par = 0 / 1 ---
-        const uint32_t inc = 0xb3u << j;
-        const uint32_t z0 = b0 ^ Y0, z1 = b1 ^ Y1;
-        const uint32_t c0 = ((L0 ^ b0) >> j) & 1u, c1 = ((L0 ^ z0 ^ b1) >> j) & 1u, c2 = ((L0 ^ z0 ^ z1 ^ b2) >> j) & 1u;
-        const uint32_t e0 = ((Y0 ^ (Y0 + inc)) >> (j + 1)) & 1u, e1 = ((Y1 ^ (Y1 + inc)) >> (j + 1)) & 1u, e2 = ((Y2 ^ (Y2 + inc)) >> (j + 1)) & 1u;
-        const uint32_t g0 = (((bs ^ Y0 ^ Y1 ^ Y2) >> (j + 1)) & 1u) ^ (c0 & e0) ^ (c1 & e1) ^ (c2 & e2);     // next plane's parity if par == 0
-        const uint32_t ee = e0 ^ e1 ^ e2;                                                                       // ... flips by this if par == 1
-        // --- the chain: popcount of the ballot -> (one LOP3.P) -> next ballot ---
-        const uint32_t par = (uint32_t)__popc(B & lt) & 1u;
-        if (j < 7) B = ballot_sel(g0, par, ee);
-        const uint32_t x0 = par ^ c0, x1 = par ^ c1, x2 = par ^ c2;
-        X0 |= x0 << j; X1 |= x1 << j; X2 |= x2 << j;
-        Y0 += x0 * inc; Y1 += x1 * inc; Y2 += x2 * inc;
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t bit = 1u << k;
+        const uint32_t z0 = b0 ^ Y0, z01 = z0 ^ b1 ^ Y1;                      // g0, g0^g1 at bit k (needed only after the vote)
+        const uint32_t B = ballot_bit(bs ^ Y0 ^ Y1 ^ Y2, bit);                // lanes whose three positions flip the parity
+        const uint32_t par = (uint32_t)__popc(B & lt) << k;                   // L (before the lane's first position) ^ L0, at bit k
+        // x = L ^ b at each position:  L_0 = par ^ L0,  L_1 = L_0 ^ g0,  L_2 = L_1 ^ g1
+        const uint32_t t0 = (par ^ L0 ^ b0) & bit;
+        const uint32_t t1 = (par ^ L0 ^ z0 ^ b1) & bit;
+        const uint32_t t2 = (par ^ L0 ^ z01 ^ b2) & bit;
+        X0 |= t0; X1 |= t1; X2 |= t2;
+        Y0 += t0 * 0xb3u; Y1 += t1 * 0xb3u; Y2 += t2 * 0xb3u;
     }
     // d = ((L ^ b) & 0xff) - L with L = X ^ b;  weight of position j is p^(n - j)
     const uint32_t n = tb + 12u, j0 = 3u * (uint32_t)lane;
@@ -133,24 +132,29 @@ __device__ __forceinline__ void coop_layout_chunk(CoopSmem::Warp& W, const uint3
         }
         row[off] = 0xf6;
         W.tb[lane] = off;
+        // the same bytes once more, in the order the hash wants them: word l of this block's row = the three payload bytes of
+        // positions 3l .. 3l+2 (parent bytes left 0) and which of the three are inside the payload.  One LDS per block and lane
+        // in the chain instead of three dependent byte loads.
+        const uint32_t tb = off;
+        W.lanew[lane][0] = 0x83u | (0x1bu << 8) | (7u << 24);
+        W.lanew[lane][1] = 7u << 24;
+        W.lanew[lane][2] = 7u << 24;
+        W.lanew[lane][3] = (0x90u << 8) | ((uint32_t)row[0] << 16) | (7u << 24);
+#pragma unroll 4
+        for (int l = 4; l < 32; ++l) {
+            const uint32_t i0 = 3u * (uint32_t)l - 11u;
+            const uint32_t v0 = i0 <= tb, v1 = i0 + 1 <= tb, v2 = i0 + 2 <= tb;       // row[tb] is the 0xf6: the last payload byte
+            const uint32_t r0 = v0 ? row[i0] : 0u, r1 = v1 ? row[i0 + 1] : 0u, r2 = v2 ? row[i0 + 2] : 0u;
+            W.lanew[lane][l] = r0 | (r1 << 8) | (r2 << 16) | ((v0 | (v1 << 1) | (v2 << 2)) << 24);
+        }
     }
 }
 
 // this lane's parent-independent payload bytes of block blk (positions 3*lane .. 3*lane+2) and which of them exist
 __device__ __forceinline__ void coop_block_bytes(const CoopSmem::Warp& W, int blk, int lane, uint32_t& tb, uint32_t& b0, uint32_t& b1, uint32_t& b2, uint32_t& vmask) {
+    const uint32_t w = W.lanew[blk][lane];
     tb = W.tb[blk];
-    const unsigned char* row = W.tokb[blk];
-    const int i0 = 3 * lane - 11;                                        // index into the row of position 3*lane; row[tb] is the 0xf6
-    const bool v0 = lane <= 3 || (uint32_t)i0 <= tb, v1 = lane <= 3 || (uint32_t)(i0 + 1) <= tb, v2 = lane <= 2 || (uint32_t)(i0 + 2) <= tb;
-    uint32_t r0 = 0, r1 = 0, r2 = 0;
-    if (lane >= 4 && v0) r0 = row[i0];
-    if (lane >= 4 && v1) r1 = row[i0 + 1];
-    if (lane >= 3 && v2) r2 = row[i0 + 2];
-    // lane 0: 0x83, 0x1b, parent | lanes 1, 2: parent | lane 3: parent, 0x90, row[0]
-    b0 = lane == 0 ? 0x83u : lane >= 4 ? r0 : 0u;
-    b1 = lane == 0 ? 0x1bu : lane == 3 ? 0x90u : lane >= 4 ? r1 : 0u;
-    b2 = lane >= 3 ? r2 : 0u;
-    vmask = (v0 ? 1u : 0u) | (v1 ? 2u : 0u) | (v2 ? 4u : 0u);
+    b0 = w & 0xffu; b1 = (w >> 8) & 0xffu; b2 = (w >> 16) & 0xffu; vmask = w >> 24;
 }
 
 // keys of a prompt's next nb (<= 32) blocks; lane j returns the key of block j (lanes >= nb: unspecified).  *last = key of

@@ -95,10 +95,11 @@ struct SubmitReq {
     const uint32_t* tok; const int64_t* tok_off; int64_t n; const uint32_t* model; uint32_t model0; const uint64_t* filter;
     double* dense; uint16_t* sp_pods; double* sp_scores; uint8_t* sp_cnt; uint8_t* has_keys;
     int rc = 0; bool done = false, promote = false; std::string err;
+    std::mutex m; std::condition_variable cv;      // each waiter sleeps on its OWN condition variable: finishing a batch wakes
+                                                   // exactly its owners (and the next leader), not every queued thread
 };
 struct SubmitQueue {
     std::mutex mu;
-    std::condition_variable cv;
     std::deque<SubmitReq*> pending;
     bool leader_active = false;
     bool enabled = true;
@@ -879,25 +880,32 @@ int submit_score(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t 
         return score_host(x, tok, tok_off, n, model, model0, filter, dense, sp_pods, sp_scores, sp_cnt, has_keys);
     if (int rc = check_csr(tok_off, n)) return rc;
     if (tok_off[n] > tok_off[0] && !tok) return fail(KVIDX_EINVAL, "NULL tokens");
-    SubmitReq me{tok, tok_off, n, model, model0, filter, dense, sp_pods, sp_scores, sp_cnt, has_keys};
+    SubmitReq me;
+    me.tok = tok; me.tok_off = tok_off; me.n = n; me.model = model; me.model0 = model0; me.filter = filter;
+    me.dense = dense; me.sp_pods = sp_pods; me.sp_scores = sp_scores; me.sp_cnt = sp_cnt; me.has_keys = has_keys;
+    bool lead;
     {
-        std::unique_lock<std::mutex> lk(q->mu);
+        std::lock_guard<std::mutex> lk(q->mu);
         q->pending.push_back(&me);
-        if (q->leader_active) {
-            q->cv.wait(lk, [&] { return me.done || me.promote; });
-            if (me.done) { if (me.rc) g_err = me.err; return me.rc; }
-            // promoted: the previous leader left with work still queued (this request among it)
-        } else q->leader_active = true;
+        lead = !q->leader_active;
+        if (lead) q->leader_active = true;
+    }
+    if (!lead) {
+        std::unique_lock<std::mutex> lk(me.m);
+        me.cv.wait(lk, [&] { return me.done || me.promote; });
+        if (me.done) { if (me.rc) g_err = me.err; return me.rc; }
+        // promoted: the previous leader left with work still queued (this request among it)
     }
     for (;;) {
         std::vector<SubmitReq*> batch;
         {
             std::unique_lock<std::mutex> lk(q->mu);
             if (me.done) {                                    // my own request is served: hand the queue to the next owner
+                SubmitReq* next = nullptr;
                 if (q->pending.empty()) q->leader_active = false;
-                else { q->pending.front()->promote = true; }
+                else next = q->pending.front();
                 lk.unlock();
-                q->cv.notify_all();
+                if (next) { std::lock_guard<std::mutex> g2(next->m); next->promote = true; next->cv.notify_one(); }
                 if (me.rc) g_err = me.err;
                 return me.rc;
             }
@@ -921,11 +929,12 @@ int submit_score(kvidx* x, const uint32_t* tok, const int64_t* tok_off, int64_t 
             q->coalesced += batch.size();
         }
         q->batches += 1;
-        {
-            std::lock_guard<std::mutex> lk(q->mu);
-            for (SubmitReq* r : batch) { r->rc = rc; if (rc) r->err = g_err; r->done = true; }
+        for (SubmitReq* r : batch) {
+            if (r == &me) { me.rc = rc; if (rc) me.err = g_err; me.done = true; continue; }
+            std::lock_guard<std::mutex> g2(r->m);             // (notify under the lock: the owner cannot return -- and destroy r -- before we are done with it)
+            r->rc = rc; if (rc) r->err = g_err; r->done = true;
+            r->cv.notify_one();
         }
-        q->cv.notify_all();
     }
 }
 

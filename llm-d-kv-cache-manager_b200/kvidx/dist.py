@@ -124,7 +124,8 @@ def score_alltoall(ix, d_tok, d_off, n, d_scores, block_size=16, model0=0, d_has
     """The ROUTED form of a sharded Score(): every key of every prompt is hashed at the origin, sent to the rank
     that owns its hash range (NCCL all-to-all), looked up there, and its 32-byte slot image sent back (second all-to-all); the
     origin then walks and scores.  No early exit, no prefix sharing: all n_blocks keys travel.  Tensors are torch CUDA
-    tensors; `ix` is a sharded handle whose stream is the current torch stream (ix.set_stream).  Returns a dict of volumes."""
+    tensors; `ix` is a sharded handle whose stream is the CURRENT torch stream, which must be a real (non-default) stream
+    -- ix.set_stream(stream.cuda_stream); handle 0 would mean the library's own stream.  Returns a dict of volumes."""
     world = dist.get_world_size()
     dev = d_tok.device
     lens = torch.div(d_off[1:n + 1] - d_off[:n], block_size, rounding_mode="floor")

@@ -78,11 +78,14 @@ def _worker_sharded(rank, world, port, q):
         assert np.array_equal(full, wl.expected_scores(doc, m))
         # the ROUTED form of the same Score() (keys to their owners, slot images back: two all-to-alls) gives the same bits
         tdev = torch.device("cuda", dev)
-        d_tok = torch.from_numpy(toks[lo:hi].reshape(-1).view(np.int32).copy()).to(tdev)
-        d_off = torch.from_numpy(off).to(tdev)
-        d_sc = torch.empty((hi - lo, 16), dtype=torch.float64, device=tdev)
-        ix.set_stream(torch.cuda.current_stream(tdev).cuda_stream)
-        vol = kd.score_alltoall(ix, d_tok, d_off, hi - lo, d_sc)
+        torch.cuda.set_device(dev)
+        st = torch.cuda.Stream(device=tdev)                     # a real stream: the library and the torch ops of the routed
+        with torch.cuda.stream(st):                             # form must share one (handle 0 means "the library's own")
+            d_tok = torch.from_numpy(toks[lo:hi].reshape(-1).view(np.int32).copy()).to(tdev)
+            d_off = torch.from_numpy(off).to(tdev)
+            d_sc = torch.empty((hi - lo, 16), dtype=torch.float64, device=tdev)
+            ix.set_stream(st.cuda_stream)
+            vol = kd.score_alltoall(ix, d_tok, d_off, hi - lo, d_sc)
         torch.cuda.synchronize()
         ix.set_stream(0)
         assert np.array_equal(d_sc.cpu().numpy(), exp) and vol["keys"] == (hi - lo) * wl.n and vol["bytes_back"] == 4 * vol["bytes_out"] > 0
