@@ -360,6 +360,25 @@ def test_synth_config2_shape_vs_oracle_and_closed_form(kernel, monkeypatch):
     assert np.array_equal(s1, wl.expected_scores(doc, m))
 
 
+def test_config2_at_its_stated_size():
+    """BASELINE config #2 as stated: 1 K prompts x 2 K tokens against a 1 M-block / 64-pod index, bit-exact vs the C++ oracle
+    (and vs the generator's closed form).  The default dispatch takes it (1000 prompts: the cooperative kernel)."""
+    wl = synth.Workload(2, 2048, 1 << 20, 64)
+    ix, co = _index_pair(capacity=(1 << 20) + 4096, max_pods=64)
+    for d0 in range(0, wl.D, 2048):
+        ev, hs, tk = wl.fill_events(d0, min(wl.D, d0 + 2048))
+        assert ix.apply_events(ev, hs, tk) == (0, 0) and co.apply_events(ev, hs, tk) == (0, 0)
+    assert ix.stats()["request_keys"] == wl.n_blocks == co.len_request() == 1 << 20
+    toks, doc, m = wl.queries(0, 1000)
+    off = np.arange(0, (len(toks) + 1) * wl.T, wl.T, dtype=np.int64)
+    s1, h1 = ix.score_batch(toks.reshape(-1), off)
+    s2, h2, _, _ = co.score_batch(toks.reshape(-1), off, n_threads=4)
+    assert np.array_equal(s1, s2) and h1.all() and np.array_equal(s1, wl.expected_scores(doc, m))
+    k1, _ = ix.hash_keys(toks[:50].reshape(-1), off[:51])
+    k2, _ = co.hash_keys(toks[:50].reshape(-1), off[:51])
+    assert np.array_equal(k1, k2)
+
+
 @pytest.mark.parametrize("kernel", ["fused", "coop", "rounds2", "classes", "classes8"])
 def test_synth_config3_shape_long_prompts(kernel, monkeypatch):
     """BASELINE config #3 shape at reduced N: 8192-token prompts (512 blocks = 16 rounds), 256 pods."""
