@@ -587,13 +587,21 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
             const uint64_t hm = home_of(key, mdl);
             const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
             uint64_t slot = hm & t.req_mask & ~1ull;
+            // A local probe fetches the aligned slot PAIR (one 64-byte DRAM access).  On a peer GPU's shard every byte crosses
+            // NVLink, and at load <= 0.25 the home slot alone decides ~9 probes out of 10: fetch it first, its neighbour only
+            // if needed (halves the NVLink bytes of a sharded step, profiles/r2_sharded_nvlink.json).
+            const bool remote = base != t.req;
             for (;;) {
                 uint4 A0, B0, A1, B1;
-                ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+                ld_slot(base + slot, peer, A0, B0);
+                if (!remote) ld_slot(base + slot + 1, peer, A1, B1);
                 uint4 A = A0, B = B0;
                 hit = slot_matches(A, B, key, mdl);
                 bool stop = hit || meta_state(B.w) == kStateEmpty;
-                if (!stop) { A = A1; B = B1; hit = slot_matches(A, B, key, mdl); stop = hit || meta_state(B.w) == kStateEmpty; }
+                if (!stop) {
+                    if (remote) ld_slot(base + slot + 1, peer, A1, B1);
+                    A = A1; B = B1; hit = slot_matches(A, B, key, mdl); stop = hit || meta_state(B.w) == kStateEmpty;
+                }
                 if (hit) { e0 = A.z; e1 = A.w; e2 = B.x; e3 = B.y; e4 = B.z; cnt = meta_count(B.w); }
                 if (stop) break;
                 slot = (slot + 2) & t.req_mask;                         // rare: displaced past the home pair
@@ -869,8 +877,10 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
                     const uint64_t hm = home_of(hk, mdl);
                     const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
                     uint64_t slot = hm & t.req_mask & ~1ull;
+                    const bool remote = base != t.req;                  // a peer's shard: home slot first, its neighbour only if needed
                     uint4 A0, B0, A1, B1;
-                    ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+                    ld_slot(base + slot, peer, A0, B0);
+                    if (!remote) ld_slot(base + slot + 1, peer, A1, B1);
                     // the next key does not depend on the probe: hash it while the probe is in flight
                     const uint64_t hn = b + 1 < nb ? hash_block16(hk, tk + (size_t)(b + 1) * BS) : 0ull;
                     SlotWords sw;
@@ -879,10 +889,14 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
                         sw.a = A0; sw.b = B0;
                         hit = slot_matches(sw.a, sw.b, hk, mdl);
                         bool stop = hit || meta_state(sw.b.w) == kStateEmpty;
-                        if (!stop) { sw.a = A1; sw.b = B1; hit = slot_matches(sw.a, sw.b, hk, mdl); stop = hit || meta_state(sw.b.w) == kStateEmpty; }
+                        if (!stop) {
+                            if (remote) ld_slot(base + slot + 1, peer, A1, B1);
+                            sw.a = A1; sw.b = B1; hit = slot_matches(sw.a, sw.b, hk, mdl); stop = hit || meta_state(sw.b.w) == kStateEmpty;
+                        }
                         if (stop) break;
                         slot = (slot + 2) & t.req_mask;                 // rare: displaced past the home pair
-                        ld_slot_pair(base + slot, peer, A0, B0, A1, B1);
+                        ld_slot(base + slot, peer, A0, B0);
+                        if (!remote) ld_slot(base + slot + 1, peer, A1, B1);
                     }
                     if (!hit) { walking = false; break; }
                     s.next(t, sw);

@@ -142,7 +142,7 @@ struct kvidx {
     int score_path = 0;            // 0 = by batch size, 1 = always the fused persistent kernel, 2 / 3 = always the plain / class round pipeline,
                                    // 4 = always the warp-per-prompt cooperative kernel
     int64_t coop_max = 2048;       // batches up to this many prompts use the warp-per-prompt cooperative kernel
-    int rounds_spec = 1;           // per-prompt rounds: run hash(t+1) beside walk(t) for small batches
+    int rounds_spec = 0;           // per-prompt rounds: run hash(t+1) beside walk(t) for small batches (measured at 65 536 prompts: 3 % slower, so off)
     int64_t rounds_spec_max = 131072;
     cudaEvent_t ev_spec_h[2][2] = {}, ev_spec_p[2][2] = {};
     int64_t zerocopy_max = 32;     // host-buffer calls up to this many prompts skip the copy engine (tokens read from pinned host memory)
