@@ -13,7 +13,10 @@ import numpy as np
 
 def one(seed):
     rng = np.random.default_rng(seed)
-    cfg = [("classes", "1"), ("classes", "2"), ("classes", "8"), ("rounds", "2"), ("classes", "4")][int(rng.integers(0, 5))]
+    cfg = [("classes", "1"), ("classes", "2"), ("classes", "8"), ("rounds", "2"), ("classes", "4"), ("coop", "1"), ("coop", "1"), ("fused", "1")][int(rng.integers(0, 8))]
+    os.environ["KVIDX_GROUP_TMA"] = str(int(rng.integers(0, 2)))
+    os.environ["KVIDX_ROUNDS_SPEC"] = str(int(rng.integers(0, 2)))
+    os.environ["KVIDX_ZEROCOPY_MAX"] = str(int(rng.choice([0, 32])))
     os.environ["KVIDX_SCORE_PATH"] = cfg[0]
     os.environ["KVIDX_ROUNDS_OVERLAP_MIN"] = "64"
     os.environ["KVIDX_ROUNDS_PARTS"] = cfg[1]
