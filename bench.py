@@ -399,13 +399,19 @@ def run_ours(args):
         d_scores.fill_(-7.0)
         step()
         parity_gate(ixx, what=mode)
+        sampler = ClockSampler(local)
+        sampler.start()                                  # started before the warm-up: nvidia-smi needs a moment (longer with N of them)
         for _ in range(max(args.warmup, 3)):
             step()
+        # keep the GPU under the same load until the sampler has produced its first rows, so that the rows taken during and
+        # around the (short) timed region are rows under load
+        t_wait = time.time()
+        while len(sampler.rows) < 2 and time.time() - t_wait < 8.0 and not os.environ.get("KVIDX_BENCH_QUICK"):
+            step()
+            torch.cuda.synchronize()
         barrier()
         launches0 = ixx.stats()["kernel_launches"]
-        sampler = ClockSampler(local)
-        sampler.start()
-        time.sleep(0.3)
+        n_before = len(sampler.rows)
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
@@ -416,9 +422,13 @@ def run_ours(args):
             b.record(stream)
         t_all1.record(stream)
         barrier()
-        clocks = sampler.stop()
         launches = ixx.stats()["kernel_launches"] - launches0
         total_ms = max_ranks(t_all0.elapsed_time(t_all1))
+        t_wait = time.time()
+        while len(sampler.rows) < n_before + 2 and time.time() - t_wait < 3.0 and not os.environ.get("KVIDX_BENCH_QUICK"):      # a few more rows under the same load
+            step()
+            torch.cuda.synchronize()
+        clocks = sampler.stop()
         step_ms = np.array([a.elapsed_time(b) for a, b in evs])
         return {"value": world * Q * args.steps / (total_ms / 1e3), "total_ms": total_ms, "step_ms": step_ms, "launches": int(launches),
                 "clocks": clocks, "step": step}
