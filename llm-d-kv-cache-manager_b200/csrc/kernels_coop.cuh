@@ -348,7 +348,7 @@ coop_score_kernel(const TableView t, const ScoreArgs a) {
             double* row = a.dense + pi * (long long)t.max_pods;
             const uint32_t P = t.max_pods;
             if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) *reinterpret_cast<double2*>(row + c2) = make_double2(-1.0, -1.0);
+                for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) st_stream_f64x2(row + c2, -1.0, -1.0, l2_policy_stream());
             } else {
                 for (uint32_t c2 = lane; c2 < P; c2 += 32) row[c2] = -1.0;
             }

@@ -28,7 +28,13 @@
 namespace kvx {
 
 constexpr int kRoundBlocks = 32;         // blocks hashed per prompt per round (== lanes per warp in kernel P)
-constexpr int kHashThreads = 256;
+#ifndef KVIDX_HASH_STAGES
+#define KVIDX_HASH_STAGES 2
+#define KVIDX_HASH_THREADS 256
+#endif
+constexpr int kHashThreads = KVIDX_HASH_THREADS;
+constexpr int kHashStages = KVIDX_HASH_STAGES;   // token blocks staged per prompt.  (4 stages x 4 warps was measured: slower -- what a launch of this kernel
+                                         // waits for is room on an SM beside kernel G's CTAs, so the smaller footprint per warp wins: scripts/ab_step.py)
 constexpr int kGroupThreads = 256;
 constexpr uint32_t kRoleSelf = 0xffffffffu;
 
@@ -95,7 +101,7 @@ constexpr int kHashChunk = 1;            // blocks staged per copy step (2 = 128
                                          // accesses but only 24 resident warps/SM -> 6 % slower; the kernel is pipe bound)
 template <int BS> struct HashSmem {
     static constexpr int kRow = kHashChunk * BS * 4 + 16;   // 144 B: the four LDS.128 of a block stay conflict free
-    unsigned char tok[kHashThreads / 32][2][32 * kRow];
+    unsigned char tok[kHashThreads / 32][kHashStages][32 * kRow];     // [warps of the CTA]: a launch with fewer warps passes that much less
 };
 
 // ---- kernel G: prefix classes ------------------------------------------------------------------------------
@@ -118,6 +124,10 @@ __device__ __forceinline__ void chunk_load(const uint32_t* sp, int nw, int lane,
     }
 }
 
+#ifndef KVIDX_GROUP_TILE
+#define KVIDX_GROUP_TILE 32
+#endif
+constexpr int kGroupTile = KVIDX_GROUP_TILE;   // live prompts a warp of kernel G takes at a time (their chunks stream through the warp one after the other)
 constexpr int kGroupRing = 4;            // chunk slots per warp: one being examined, two in flight, the anchor (deeper rings measured: slower)
 struct GroupSmem {
     uint4 ring[kGroupThreads / 32][kGroupRing][4][32];                       // 64 KB
@@ -136,6 +146,7 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     unsigned long long* bar = reinterpret_cast<GroupSmem*>(smem_raw_g)->bar[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     uint32_t tma_pending = 0, tma_phase = 0;          // per rotating slot: a bulk copy is in flight / parity of its next wait
+    const uint64_t l2pol = l2_policy_stream();
     if (TMA) {
         if (lane == 0) for (int s = 0; s < kGroupRing - 1; ++s) mbar_init(&bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -145,9 +156,9 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     const unsigned int n_act = rb.n_act[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0) { rb.n_act[cur ^ 1] = 0; rb.n_hl[0] = 0; rb.n_hl[1] = 0; rb.n_hl[2] = 0; rb.n_hl[3] = 0; }   // lists built below / by G2
     const unsigned int total_warps = gridDim.x * (kGroupThreads / 32);
-    for (unsigned int w = blockIdx.x * (kGroupThreads / 32) + (threadIdx.x >> 5); w * 32u < n_act; w += total_warps) {
-        const unsigned int i = w * 32u + lane;
-        const bool have = i < n_act;
+    for (unsigned int w = blockIdx.x * (kGroupThreads / 32) + (threadIdx.x >> 5); w * (unsigned)kGroupTile < n_act; w += total_warps) {
+        const unsigned int i = w * (unsigned)kGroupTile + lane;
+        const bool have = lane < kGroupTile && i < n_act;
         uint32_t p = 0, srcp = kRoleSelf, mdl = a.model0;
         int nb = 0; bool more = false;
         uint64_t hprev = t.init_hash;
@@ -197,7 +208,7 @@ group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                     uint4* dst = &ring[slot][c][lane];
                     if (w0 < nw) {
                         if (TMA && al) {}
-                        else if (al) cp_async_16(smem_addr(dst), sp + w0);
+                        else if (al) cp_async_16_stream(smem_addr(dst), sp + w0, l2pol);
                         else *dst = make_uint4(__ldg(sp + w0), __ldg(sp + w0 + 1), __ldg(sp + w0 + 2), __ldg(sp + w0 + 3));
                     } else *dst = make_uint4(0, 0, 0, 0);
                 }
@@ -446,14 +457,15 @@ group_lists_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
 
 // ---- kernel H ---------------------------------------------------------------------------------
 template <int BS>
-__global__ void __launch_bounds__(kHashThreads, 4)
-hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+__global__ void __launch_bounds__(kHashThreads, 3)
+hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int prefetch) {
     static_assert(BS == 16, "staging pattern is written for 16-token blocks");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using SM = HashSmem<BS>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned int n_hl = rb.n_hl[0];                                 // representatives this round (kernel G)
+    const uint64_t l2pol = l2_policy_stream();
     {   // the election map, grp and nfol are dead until the next round's kernel G: clear them here instead of three memsets
         uint4* m4 = reinterpret_cast<uint4*>(rb.map);
         const size_t nm = ((size_t)rb.map_mask + 1 + rb.part_size) / 4;   // map + grp are contiguous; sizes are multiples of 4 words
@@ -461,8 +473,8 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
         uint32_t* f4 = reinterpret_cast<uint32_t*>(rb.nfol);
         for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < rb.part_size / 4; x += (size_t)gridDim.x * blockDim.x) f4[x] = 0u;
     }
-    const unsigned int total_warps = gridDim.x * (kHashThreads / 32);
-    for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_hl; w += total_warps) {
+    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
+    for (unsigned int w = blockIdx.x * (blockDim.x / 32) + wid; w * 32u < n_hl; w += total_warps) {
         const unsigned int i = w * 32u + lane;                            // position in the representative list
         const bool have = i < n_hl;
         const uint32_t p = have ? rb.act[cur][rb.hl[i]] : 0u;
@@ -480,6 +492,16 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
             h = round == 0 ? t.init_hash : rb.hstate[p];
         }
         const int nb_max = __reduce_max_sync(0xffffffffu, nb);
+        // The chain below consumes one 64-byte block per prompt per ~0.6 us and stages only one block ahead: pull the whole
+        // chunk (<= 2 KB per prompt) towards L2 now, so that the staging copies find it there instead of paying a loaded DRAM
+        // round trip per block.
+        if (prefetch && have) {
+            const char* pb = reinterpret_cast<const char*>(src);
+            for (int o = 128; o < nb * BS * 4; o += 128) {
+                if (prefetch == 2) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pb + o));
+                else asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + o));
+            }
+        }
         // stage chunk c (kHashChunk blocks) of every lane's prompt: 4*kHashChunk lanes move one prompt's contiguous bytes.
         auto stage = [&](int s, int c) {
             const int b0 = c * kHashChunk;
@@ -495,7 +517,7 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
                 const unsigned long long sp = __shfl_sync(0xffffffffu, srcv, q);
                 const int nby = kHashChunk == 1 ? BS * 4 : __shfl_sync(0xffffffffu, nbytes, q);
                 if (sp && (lane % LPP) * 16 < nby)
-                    cp_async_16(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane % LPP) * 16]), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16);
+                    cp_async_16_stream(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane % LPP) * 16]), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16, l2pol);
             }
             cp_async_commit();
             if (issue && !aligned) {
@@ -504,18 +526,19 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
                 for (int j = 0; j < nbytes / 4; ++j) dst[j] = __ldg(g + j);
             }
         };
-        stage(0, 0);
+#pragma unroll
+        for (int c = 0; c < kHashStages - 1; ++c) stage(c, c);
         const int nchunks = (nb_max + kHashChunk - 1) / kHashChunk;
         for (int c = 0; c < nchunks; ++c) {
-            stage((c + 1) & 1, c + 1);
-            cp_async_wait<1>();
+            stage((c + kHashStages - 1) % kHashStages, c + kHashStages - 1);
+            cp_async_wait<kHashStages - 1>();
             __syncwarp();
 #pragma unroll
             for (int u = 0; u < kHashChunk; ++u) {
                 const int b = c * kHashChunk + u;
                 Fnv f;
                 f.begin_block(h, BS);
-                const uint4* tp = reinterpret_cast<const uint4*>(&sm.tok[wid][c & 1][lane * SM::kRow + u * BS * 4]);
+                const uint4* tp = reinterpret_cast<const uint4*>(&sm.tok[wid][c % kHashStages][lane * SM::kRow + u * BS * 4]);
                 const uint4 v0 = tp[0], v1 = tp[1];
                 f.token(v0.x); f.token(v0.y); f.token(v0.z); f.token(v0.w);
                 const uint4 v2 = tp[2];
@@ -707,7 +730,7 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
                 double* row = a.dense + (long long)p * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) *reinterpret_cast<double2*>(row + c2) = make_double2(-1.0, -1.0);
+                    for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) st_stream_f64x2(row + c2, -1.0, -1.0, l2_policy_stream());
                 } else {
                     for (uint32_t c2 = lane; c2 < P; c2 += 32) row[c2] = -1.0;
                 }
@@ -783,7 +806,7 @@ __device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArg
                 double* row = a.dense + (long long)pp * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
+                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
                 } else {
                     for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                 }
@@ -819,11 +842,12 @@ __device__ __forceinline__ uint64_t hash_block16(uint64_t parent, const uint32_t
     return f.end_block();
 }
 constexpr int kDetachBlocks = 3;          // blocks a partial follower walks alone inside the round before it is re-queued
-struct DetachSmem { double sc[256 / 32][kMaxEnt][32]; uint16_t pod[256 / 32][kMaxEnt][32]; };
+struct DetachWarp { double sc[kMaxEnt][32]; uint16_t pod[kMaxEnt][32]; };     // per warp (dynamic shared memory: warps of the CTA x this)
 template <int BS>
-__device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int trace, DetachSmem& sm,
+__device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int trace, DetachWarp* smw,
                                              const unsigned int bid, const unsigned int nbl) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    DetachWarp& sm = smw[wid];
     const unsigned int n_dl = rb.n_hl[2];
     const PromptState* pst_rd = rb.pst[round & 1];
     PromptState* pst_cur = rb.pst[round & 1];
@@ -922,7 +946,7 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
                 for (uint32_t q = 0; q < s.k; ++q) { ps.sc[q] = s.sc[q]; ps.pod[q] = s.pod[q]; ps.bt[q] = 0xffu; }
             }
         }
-        for (uint32_t q = 0; q < s.k; ++q) { sm.sc[wid][q][lane] = s.sc[q]; sm.pod[wid][q][lane] = s.pod[q]; }
+        for (uint32_t q = 0; q < s.k; ++q) { sm.sc[q][lane] = s.sc[q]; sm.pod[q][lane] = s.pod[q]; }
         __syncwarp();
         uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
         while (dm) {
@@ -933,15 +957,15 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
                 double* row = a.dense + (long long)pp * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
+                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
                 } else {
                     for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                 }
                 __syncwarp();
-                if ((uint32_t)lane < pk) { const uint32_t pd = sm.pod[wid][lane][l]; if (pd < P) row[pd] = sm.sc[wid][lane][l]; }
+                if ((uint32_t)lane < pk) { const uint32_t pd = sm.pod[lane][l]; if (pd < P) row[pd] = sm.sc[lane][l]; }
             }
             if (a.sp_cnt) {
-                if ((uint32_t)lane < pk) { a.sp_pods[(long long)pp * kMaxEnt + lane] = sm.pod[wid][lane][l]; a.sp_scores[(long long)pp * kMaxEnt + lane] = sm.sc[wid][lane][l]; }
+                if ((uint32_t)lane < pk) { a.sp_pods[(long long)pp * kMaxEnt + lane] = sm.pod[lane][l]; a.sp_scores[(long long)pp * kMaxEnt + lane] = sm.sc[lane][l]; }
                 if (lane == 0) a.sp_cnt[pp] = (uint8_t)pk;
             }
             if (a.has_keys && lane == 0) a.has_keys[pp] = 1;
@@ -955,7 +979,8 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
 template <int BS>
 __global__ void __launch_bounds__(256)
 finish_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int detach, const int trace) {
-    __shared__ DetachSmem sm;
+    extern __shared__ __align__(16) unsigned char smem_raw_f[];
+    DetachWarp* sm = reinterpret_cast<DetachWarp*>(smem_raw_f);
     if (!detach) { resolve_round(t, a, rb, cur, round, blockIdx.x, gridDim.x); return; }
     // odd CTAs take the followers, even CTAs the partial followers: the two latency chains run side by side
     const unsigned int half = gridDim.x / 2;

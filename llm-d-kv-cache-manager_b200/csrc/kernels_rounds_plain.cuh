@@ -108,7 +108,7 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
                 const unsigned long long sp = __shfl_sync(0xffffffffu, srcv, q);
                 const int nby = kHashChunk == 1 ? BS * 4 : __shfl_sync(0xffffffffu, nbytes, q);
                 if (sp && (lane % LPP) * 16 < nby)
-                    cp_async_16(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane % LPP) * 16]), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16);
+                    cp_async_16_stream(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane % LPP) * 16]), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16, l2_policy_stream());
             }
             cp_async_commit();
             if (issue && !aligned) {
@@ -311,7 +311,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 double* row = a.dense + (long long)pp * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
+                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
                 } else {
                     for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                 }

@@ -57,6 +57,33 @@ __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// L2 eviction policy for data that is read or written exactly once per step (the token stream, the dense result rows):
+// evict_first keeps it from flushing what the latency-bound kernels of a round hand to each other (lists, walk states, keys)
+// and the index slots out of the 126 MB L2.
+#ifndef KVIDX_L2_STREAM
+#define KVIDX_L2_STREAM 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t pol = 0;
+#if KVIDX_L2_STREAM
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+    return pol;
+}
+__device__ __forceinline__ void cp_async_16_stream(uint32_t dst, const void* src, uint64_t pol) {
+#if KVIDX_L2_STREAM
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+#else
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void st_stream_f64x2(double* p, double a, double b, uint64_t pol) {
+#if KVIDX_L2_STREAM
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(a), "d"(b), "l"(pol) : "memory");
+#else
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+#endif
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
@@ -138,7 +165,7 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
                     double* row = a.dense + ppi * (long long)t.max_pods;
                     const uint32_t P = t.max_pods;
                     if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                        for (uint32_t c = lane * 2; c < P; c += 64) *reinterpret_cast<double2*>(row + c) = make_double2(-1.0, -1.0);
+                        for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
                     } else {
                         for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                     }
@@ -191,7 +218,7 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
         for (int r = 0; r < 4; ++r) {                           // 8 prompts x 64 B per instruction
             const int p = 8 * r + (lane >> 2);
             const unsigned long long sp = __shfl_sync(0xffffffffu, srcv, p);
-            if (sp && !(KVX_ABLATE & 4)) cp_async_16(smem_addr(&W.tok[s][p * SM::kRow + (lane & 3) * 16]), reinterpret_cast<const char*>(sp) + (lane & 3) * 16);
+            if (sp && !(KVX_ABLATE & 4)) cp_async_16_stream(smem_addr(&W.tok[s][p * SM::kRow + (lane & 3) * 16]), reinterpret_cast<const char*>(sp) + (lane & 3) * 16, l2_policy_stream());
         }
         cp_async_commit();
         if (issue && !aligned) {                                // unaligned prompt start: this lane copies its own block

@@ -161,6 +161,14 @@ struct kvidx {
     int rounds_overlap = 1;        // run the two halves of a large batch on two streams
     int64_t rounds_overlap_min = 65536;
     cudaStream_t aux_stream[kMaxParts - 1] = {}; cudaEvent_t ev_fork = nullptr, ev_join[kMaxParts - 1] = {};
+    // group_serial: every part's kernel G runs on ONE stream, one after the other at full bandwidth, while the other parts'
+    // latency-bound kernels (G2, H, P, R) run beside it on their own streams (otherwise the parts drift into lock step: all in
+    // G sharing the bandwidth, then all in the short kernels with DRAM idle -- scripts/timeline.py)
+    int group_serial = 2, group_serial_grid = 2;
+    int group_ctas = 0;            // > 0: CTAs of one part's kernel G (all parts' G CTAs resident at once: nothing queues behind them)
+    int hash_prefetch = 0;         // kernel H pulls its chunks towards L2 before the chain starts (1; 2: evict_last)
+    int small_cta = 256;           // threads per CTA of the short kernels (G2, H, P, R): small CTAs fit into what kernel G's CTAs leave of an SM
+    cudaStream_t g_stream = nullptr, hp_stream[kMaxParts] = {}, lp_stream[kMaxParts] = {}; cudaEvent_t ev_g[kMaxParts] = {}, ev_r[kMaxParts] = {};
 };
 
 namespace {
@@ -419,31 +427,43 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         for (int q = 1; q < np; ++q) CK(cudaStreamWaitEvent(strm[q], x->ev_fork, 0));
     }
     const auto t_enq = std::chrono::steady_clock::now();
+    // Where kernel G runs: 0 the part's stream; 1 ONE stream for every part's G; 2 a low-priority stream per part, with the part's
+    // short kernels on a high-priority one (a CTA slot that frees up goes to a waiting latency-bound kernel before the next G CTA).
+    const int gmode = np > 1 ? x->group_serial : 0;
+    cudaStream_t sS[kMaxParts], sG[kMaxParts];
+    for (int q = 0; q < kMaxParts; ++q) { sS[q] = gmode == 2 ? x->hp_stream[q] : strm[q]; sG[q] = gmode == 2 ? x->lp_stream[q] : gmode == 1 ? x->g_stream : strm[q]; }
+    if (gmode == 1) CK(cudaStreamWaitEvent(x->g_stream, x->ev_fork, 0));
+    if (gmode == 2) for (int q = 0; q < np; ++q) { CK(cudaStreamWaitEvent(sS[q], x->ev_fork, 0)); CK(cudaStreamWaitEvent(sG[q], x->ev_fork, 0)); }
+    const int T = x->small_cta, W = T / 32, kf = 256 / T;        // threads / warps of the short kernels' CTAs; CTAs per 256 threads
     for (int64_t r = 0; r < rounds; ++r) {
         const int cur = (int)(r & 1);
         for (int q = 0; q < np; ++q) {
             const int64_t m = psz[q];
             if (m <= 0) continue;
-            const unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads - 1) / kGroupThreads, (int64_t)x->sm_count * (np == 1 ? 3 : x->rounds_grid[0]));
-            if (x->group_tma) group_round_kernel<16, true><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
-            else group_round_kernel<16, false><<<ggrid, kGroupThreads, sizeof(GroupSmem), strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
-            const unsigned lgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : x->rounds_grid[1]));
-            group_lists_kernel<16><<<lgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2);
+            unsigned ggrid = (unsigned)std::min<int64_t>((m + kGroupThreads / 32 * kGroupTile - 1) / (kGroupThreads / 32 * kGroupTile), (int64_t)x->sm_count * (np == 1 ? 3 : gmode == 1 ? x->group_serial_grid : x->rounds_grid[0]));
+            if (x->group_ctas > 0 && np > 1) ggrid = std::min<unsigned>(ggrid, (unsigned)x->group_ctas);
+            if (gmode && r > 0) CK(cudaStreamWaitEvent(sG[q], x->ev_r[q], 0));       // this part's previous round has built the live list
+            if (x->group_tma) group_round_kernel<16, true><<<ggrid, kGroupThreads, sizeof(GroupSmem), sG[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
+            else group_round_kernel<16, false><<<ggrid, kGroupThreads, sizeof(GroupSmem), sG[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup);
+            if (gmode) { CK(cudaEventRecord(x->ev_g[q], sG[q])); CK(cudaStreamWaitEvent(sS[q], x->ev_g[q], 0)); }
+            const unsigned lgrid = (unsigned)std::min<int64_t>((m + T - 1) / T, (int64_t)x->sm_count * kf * (np <= 2 ? 8 : x->rounds_grid[1]));
+            group_lists_kernel<16><<<lgrid, T, 0, sS[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2);
         }
         for (int q = 0; q < np; ++q) {
             const int64_t m = psz[q];
             if (m <= 0) continue;
-            const unsigned hgrid = (unsigned)std::min<int64_t>((m + kHashThreads - 1) / kHashThreads, (int64_t)x->sm_count * (np == 1 ? 4 : x->rounds_grid[2]));
-            hash_round_kernel<16><<<hgrid, kHashThreads, sizeof(HashSmem<16>), strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
-            const unsigned wgrid = (unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)x->sm_count * (np == 1 ? 8 : x->rounds_grid[3]));
-            walk_round_kernel<<<wgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r);
-            const unsigned rgrid = (unsigned)std::min<int64_t>((m + 255) / 256, (int64_t)x->sm_count * (np <= 2 ? 8 : x->rounds_grid[4]));
-            finish_round_kernel<16><<<rgrid, 256, 0, strm[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2, x->rounds_trace);
+            const unsigned hgrid = (unsigned)std::min<int64_t>((m + T - 1) / T, (int64_t)x->sm_count * kf * (np == 1 ? 4 : x->rounds_grid[2]));
+            hash_round_kernel<16><<<hgrid, T, sizeof(HashSmem<16>) / (kHashThreads / 32) * W, sS[q]>>>(x->tv, a, rb[q], cur, (int)r, x->hash_prefetch);
+            const unsigned wgrid = (unsigned)std::min<int64_t>((m + W - 1) / W, (int64_t)x->sm_count * kf * (np == 1 ? 8 : x->rounds_grid[3]));
+            walk_round_kernel<<<wgrid, T, 0, sS[q]>>>(x->tv, a, rb[q], cur, (int)r);
+            const unsigned rgrid = (unsigned)std::min<int64_t>((m + T - 1) / T, (int64_t)x->sm_count * kf * (np <= 2 ? 8 : x->rounds_grid[4]));
+            finish_round_kernel<16><<<rgrid, T, sizeof(DetachWarp) * W, sS[q]>>>(x->tv, a, rb[q], cur, (int)r, x->rounds_dedup >= 2, x->rounds_trace);
+            if (gmode && r + 1 < rounds) CK(cudaEventRecord(x->ev_r[q], sS[q]));
             x->launches += 5;
             if (x->rounds_trace == 1) {      // debugging aid: list sizes of this round (synchronises)
                 unsigned int c[8];
-                CK(cudaMemcpyAsync(c, rb[q].n_act, sizeof c, cudaMemcpyDeviceToHost, strm[q]));
-                CK(cudaStreamSynchronize(strm[q]));
+                CK(cudaMemcpyAsync(c, rb[q].n_act, sizeof c, cudaMemcpyDeviceToHost, sS[q]));
+                CK(cudaStreamSynchronize(sS[q]));
                 fprintf(stderr, "[kvidx rounds] round %lld part %d: live %u -> representatives %u, followers %u, partial %u (%u blocks walked alone) -> next %u\n",
                         (long long)r, q, c[cur], c[2], c[3], c[4], c[5], c[cur ^ 1]);
             }
@@ -452,7 +472,8 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
     if (x->rounds_trace == 2) fprintf(stderr, "[kvidx rounds] host enqueue of %lld rounds x %d parts: %.3f ms\n", (long long)rounds, np,
                                       std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq).count());
     CK(cudaGetLastError());
-    for (int q = 1; q < np; ++q) { CK(cudaEventRecord(x->ev_join[q - 1], strm[q])); CK(cudaStreamWaitEvent(st, x->ev_join[q - 1], 0)); }
+    for (int q = 1; q < np; ++q) { CK(cudaEventRecord(x->ev_join[q - 1], sS[q])); CK(cudaStreamWaitEvent(st, x->ev_join[q - 1], 0)); }
+    if (gmode == 2) { CK(cudaEventRecord(x->ev_g[0], sS[0])); CK(cudaStreamWaitEvent(st, x->ev_g[0], 0)); }
     return 0;
 }
 
@@ -1025,6 +1046,16 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
         CK(cudaEventCreateWithFlags(&x->ev_join[q], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&x->ev_fork, cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&x->g_stream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int q = 0; q < kMaxParts; ++q) {
+            CK(cudaStreamCreateWithPriority(&x->hp_stream[q], cudaStreamNonBlocking, hi));
+            CK(cudaStreamCreateWithPriority(&x->lp_stream[q], cudaStreamNonBlocking, lo));
+        }
+    }
+    for (int q = 0; q < kMaxParts; ++q) { CK(cudaEventCreateWithFlags(&x->ev_g[q], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&x->ev_r[q], cudaEventDisableTiming)); }
     CK(cudaEventCreateWithFlags(&x->ev_write, cudaEventDisableTiming));
     for (int a_ = 0; a_ < 2; ++a_) for (int b_ = 0; b_ < 2; ++b_) {
         CK(cudaEventCreateWithFlags(&x->ev_spec_h[a_][b_], cudaEventDisableTiming));
@@ -1083,6 +1114,11 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
     if (const char* k = getenv("KVIDX_HOST_CHUNK_TOKENS")) x->host_chunk_tokens = std::max<int64_t>(1 << 16, atoll(k));
     if (const char* k = getenv("KVIDX_ROUNDS_TRACE")) x->rounds_trace = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
+    if (const char* k = getenv("KVIDX_GROUP_SERIAL")) x->group_serial = atoi(k);
+    if (const char* k = getenv("KVIDX_HASH_PREFETCH")) x->hash_prefetch = atoi(k);
+    if (const char* k = getenv("KVIDX_GROUP_CTAS")) x->group_ctas = atoi(k);
+    if (const char* k = getenv("KVIDX_SMALL_CTA")) { const int v = atoi(k); if (v == 32 || v == 64 || v == 128 || v == 256) x->small_cta = v; }
+    if (const char* k = getenv("KVIDX_GROUP_SERIAL_GRID")) x->group_serial_grid = std::max(1, atoi(k));
     if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_OVERLAP_MIN")) x->rounds_overlap_min = atoll(k);
     if (const char* k = getenv("KVIDX_WRITE_PHASE1")) x->write_phase1 = atoi(k);
@@ -1161,6 +1197,9 @@ void kvidx_destroy(kvidx_t* x) {
         if (x->ev_join[q]) cudaEventDestroy(x->ev_join[q]);
     }
     if (x->ev_fork) cudaEventDestroy(x->ev_fork);
+    if (x->g_stream) cudaStreamDestroy(x->g_stream);
+    for (int q = 0; q < kMaxParts; ++q) { if (x->hp_stream[q]) cudaStreamDestroy(x->hp_stream[q]); if (x->lp_stream[q]) cudaStreamDestroy(x->lp_stream[q]); }
+    for (int q = 0; q < kMaxParts; ++q) { if (x->ev_g[q]) cudaEventDestroy(x->ev_g[q]); if (x->ev_r[q]) cudaEventDestroy(x->ev_r[q]); }
     if (x->ev_write) cudaEventDestroy(x->ev_write);
     for (int a_ = 0; a_ < 2; ++a_) for (int b_ = 0; b_ < 2; ++b_) {
         if (x->ev_spec_h[a_][b_]) cudaEventDestroy(x->ev_spec_h[a_][b_]);
