@@ -190,6 +190,7 @@ __device__ __forceinline__ int coop_hash_chunk(const CoopSmem& sm, CoopSmem::War
 template <int BS>
 __global__ void __launch_bounds__(kCoopThreads)
 coop_score_kernel(const TableView t, const ScoreArgs a) {
+    const uint64_t l2pol = l2_policy_stream();
     static_assert(BS == 16, "payload layout is written for 16-token blocks");
     extern __shared__ __align__(128) unsigned char smem_raw_c[];
     CoopSmem& sm = *reinterpret_cast<CoopSmem*>(smem_raw_c);
@@ -348,7 +349,7 @@ coop_score_kernel(const TableView t, const ScoreArgs a) {
             double* row = a.dense + pi * (long long)t.max_pods;
             const uint32_t P = t.max_pods;
             if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) st_stream_f64x2(row + c2, -1.0, -1.0, l2_policy_stream());
+                for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) st_stream_f64x2(row + c2, -1.0, -1.0, l2pol);
             } else {
                 for (uint32_t c2 = lane; c2 < P; c2 += 32) row[c2] = -1.0;
             }

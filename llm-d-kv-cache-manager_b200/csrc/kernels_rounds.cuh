@@ -578,6 +578,7 @@ __global__ void __launch_bounds__(256)
 walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
     const int lane = threadIdx.x & 31;
     const unsigned int n_a = rb.n_hl[0];
+    const uint64_t l2pol = l2_policy_stream();
     const size_t kstride = (size_t)a.n_prompts;
     const bool peer = t.shard_bits != 0;
     const PromptState* pst_prev = rb.pst[(round & 1) ^ 1];
@@ -730,7 +731,7 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
                 double* row = a.dense + (long long)p * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) st_stream_f64x2(row + c2, -1.0, -1.0, l2_policy_stream());
+                    for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) st_stream_f64x2(row + c2, -1.0, -1.0, l2pol);
                 } else {
                     for (uint32_t c2 = lane; c2 < P; c2 += 32) row[c2] = -1.0;
                 }
@@ -752,7 +753,7 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
 // walk state stays where the representative left it (src).  Representative finished: same pods, same scores -- the warp
 // writes the follower's result from the representative's final state.
 __device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round,
-                                              const unsigned int bid, const unsigned int nbl) {
+                                              const unsigned int bid, const unsigned int nbl, const uint64_t l2pol) {
     const int lane = threadIdx.x & 31;
     {   // kernel P is done with need_snap: clear it for the next round
         uint32_t* f4 = reinterpret_cast<uint32_t*>(rb.need_snap);
@@ -806,7 +807,7 @@ __device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArg
                 double* row = a.dense + (long long)pp * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
+                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2pol);
                 } else {
                     for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                 }
@@ -845,7 +846,7 @@ constexpr int kDetachBlocks = 3;          // blocks a partial follower walks alo
 struct DetachWarp { double sc[kMaxEnt][32]; uint16_t pod[kMaxEnt][32]; };     // per warp (dynamic shared memory: warps of the CTA x this)
 template <int BS>
 __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int trace, DetachWarp* smw,
-                                             const unsigned int bid, const unsigned int nbl) {
+                                             const unsigned int bid, const unsigned int nbl, const uint64_t l2pol) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     DetachWarp& sm = smw[wid];
     const unsigned int n_dl = rb.n_hl[2];
@@ -957,7 +958,7 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
                 double* row = a.dense + (long long)pp * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
+                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2pol);
                 } else {
                     for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                 }
@@ -981,12 +982,13 @@ __global__ void __launch_bounds__(256)
 finish_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int detach, const int trace) {
     extern __shared__ __align__(16) unsigned char smem_raw_f[];
     DetachWarp* sm = reinterpret_cast<DetachWarp*>(smem_raw_f);
-    if (!detach) { resolve_round(t, a, rb, cur, round, blockIdx.x, gridDim.x); return; }
+    const uint64_t l2pol = l2_policy_stream();
+    if (!detach) { resolve_round(t, a, rb, cur, round, blockIdx.x, gridDim.x, l2pol); return; }
     // odd CTAs take the followers, even CTAs the partial followers: the two latency chains run side by side
     const unsigned int half = gridDim.x / 2;
-    if (gridDim.x < 2) { resolve_round(t, a, rb, cur, round, 0, 1); detach_round<BS>(t, a, rb, cur, round, trace, sm, 0, 1); }
-    else if (blockIdx.x & 1) { if (blockIdx.x / 2 < half) resolve_round(t, a, rb, cur, round, blockIdx.x / 2, half); }
-    else detach_round<BS>(t, a, rb, cur, round, trace, sm, blockIdx.x / 2, (gridDim.x + 1) / 2);
+    if (gridDim.x < 2) { resolve_round(t, a, rb, cur, round, 0, 1, l2pol); detach_round<BS>(t, a, rb, cur, round, trace, sm, 0, 1, l2pol); }
+    else if (blockIdx.x & 1) { if (blockIdx.x / 2 < half) resolve_round(t, a, rb, cur, round, blockIdx.x / 2, half, l2pol); }
+    else detach_round<BS>(t, a, rb, cur, round, trace, sm, blockIdx.x / 2, (gridDim.x + 1) / 2, l2pol);
 }
 
 // List setup + a 64-bit fingerprint of every prompt's first block.  The batch is then radix-sorted by fingerprint so

@@ -61,20 +61,28 @@ template <int BS> struct HashSmem {
 };
 
 // ---- kernel H ---------------------------------------------------------------------------------
-template <int BS>
+// PM (prompt-major keys): key of block j of list slot i at keys[i * 32 + j] -- what the warp-per-prompt kernel P reads in one
+// coalesced 256-byte load; block-major (keys[j * n_prompts + i]) is what the lane-per-prompt kernel P wants.
+// NS: token blocks staged per prompt (NS - 1 copies in flight ahead of the chain).  With 2 a launch lasts 32 x max(FNV of a block,
+// one loaded DRAM round trip) -- fine when the list fills the machine, the floor of the round (~46 us) when it does not: the
+// warp-per-prompt configuration stages 3 and runs 128-thread CTAs (55 KB each, four per SM).
+template <int BS, bool PM, int NS>
 __global__ void __launch_bounds__(kHashThreads, 4)
 hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
     static_assert(BS == 16, "staging pattern is written for 16-token blocks");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using SM = HashSmem<BS>;
-    SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned char* const wtok = smem_raw + (size_t)wid * NS * 32 * SM::kRow;          // this warp's NS stages of 32 rows
+    const uint32_t wbase = smem_addr(wtok);         // 32-bit shared-window address of the warp's stages
+    const uint64_t l2pol = l2_policy_stream();      // created once, in uniform control flow (a policy built inside the divergent
+                                                    // staging branch made ptxas 12.9 emit an LDGSTS with an unset descriptor: illegal instruction)
     // the list this kernel works on: the round's own list, or (speculative schedule) the list of the round before
     const int src = rb.spec ? (round == 0 ? 0 : ((round - 1) & 1)) : cur;
     const unsigned int n_act = rb.n_act[src];
     if (!rb.spec && blockIdx.x == 0 && threadIdx.x == 0) rb.n_act[cur ^ 1] = 0;      // next round's list starts empty
-    const unsigned int total_warps = gridDim.x * (kHashThreads / 32);
-    for (unsigned int w = blockIdx.x * (kHashThreads / 32) + wid; w * 32u < n_act; w += total_warps) {
+    const unsigned int total_warps = gridDim.x * (blockDim.x / 32);
+    for (unsigned int w = blockIdx.x * (blockDim.x / 32) + wid; w * 32u < n_act; w += total_warps) {
         const unsigned int i = w * 32u + lane;                            // slot in the active list
         const bool have = i < n_act;
         const uint32_t p = have ? rb.act[src][i] : 0u;
@@ -108,27 +116,28 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
                 const unsigned long long sp = __shfl_sync(0xffffffffu, srcv, q);
                 const int nby = kHashChunk == 1 ? BS * 4 : __shfl_sync(0xffffffffu, nbytes, q);
                 if (sp && (lane % LPP) * 16 < nby)
-                    cp_async_16_stream(smem_addr(&sm.tok[wid][s][q * SM::kRow + (lane % LPP) * 16]), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16, l2_policy_stream());
+                    cp_async_16_stream(wbase + (uint32_t)(s * 32 * SM::kRow + q * SM::kRow + (lane % LPP) * 16), reinterpret_cast<const char*>(sp) + (lane % LPP) * 16, l2pol);
             }
             cp_async_commit();
             if (issue && !aligned) {
-                uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.tok[wid][s][lane * SM::kRow]);
+                uint32_t* dst = reinterpret_cast<uint32_t*>(wtok + (size_t)s * 32 * SM::kRow + lane * SM::kRow);
                 const uint32_t* g = src + (size_t)b0 * BS;
                 for (int j = 0; j < nbytes / 4; ++j) dst[j] = __ldg(g + j);
             }
         };
-        stage(0, 0);
+#pragma unroll
+        for (int c = 0; c < NS - 1; ++c) stage(c, c);
         const int nchunks = (nb_max + kHashChunk - 1) / kHashChunk;
         for (int c = 0; c < nchunks; ++c) {
-            stage((c + 1) & 1, c + 1);
-            cp_async_wait<1>();
+            stage((c + NS - 1) % NS, c + NS - 1);
+            cp_async_wait<NS - 1>();
             __syncwarp();
 #pragma unroll
             for (int u = 0; u < kHashChunk; ++u) {
                 const int b = c * kHashChunk + u;
                 Fnv f;
                 f.begin_block(h, BS);
-                const uint4* tp = reinterpret_cast<const uint4*>(&sm.tok[wid][c & 1][lane * SM::kRow + u * BS * 4]);
+                const uint4* tp = reinterpret_cast<const uint4*>(wtok + (size_t)(c % NS) * 32 * SM::kRow + lane * SM::kRow + u * BS * 4);
                 const uint4 v0 = tp[0], v1 = tp[1];
                 f.token(v0.x); f.token(v0.y); f.token(v0.z); f.token(v0.w);
                 const uint4 v2 = tp[2];
@@ -137,7 +146,7 @@ hash_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
                 f.token(v2.x); f.token(v2.y); f.token(v2.z); f.token(v2.w);
                 f.token(v3.x); f.token(v3.y); f.token(v3.z); f.token(v3.w);
                 const uint64_t key = f.end_block();
-                if (b < nb) { h = key; rb.keys[(size_t)b * a.n_prompts + i] = key; }
+                if (b < nb) { h = key; rb.keys[PM ? (size_t)i * kRoundBlocks + b : (size_t)b * a.n_prompts + i] = key; }
             }
         }
         cp_async_wait<0>();
@@ -171,6 +180,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
     if (threadIdx.x < 16) sm.weight[threadIdx.x] = t.weight[threadIdx.x];
     __syncthreads();
     const unsigned int n_act = rb.n_act[cur];
+    const uint64_t l2pol = l2_policy_stream();
     const size_t kstride = (size_t)a.n_prompts;
     const bool peer = t.shard_bits != 0;
     const unsigned int total_warps = gridDim.x * (kProbeThreads / 32);
@@ -311,7 +321,7 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
                 double* row = a.dense + (long long)pp * t.max_pods;
                 const uint32_t P = t.max_pods;
                 if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
+                    for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2pol);
                 } else {
                     for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                 }
@@ -325,6 +335,171 @@ probe_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
             if (a.has_keys && lane == 0) a.has_keys[pp] = (round > 0) || (pmeta & 63u) > 0;
         }
         __syncwarp();
+    }
+}
+
+// ---- kernel P, warp per prompt -----------------------------------------------------------------
+// For batches of a few ten thousand prompts the lane-per-prompt kernel above is a latency chain: a warp walks its 32 prompts
+// through 32 dependent probe -> score iterations (~2 us each) while most of the machine idles (scripts/timeline.py: 64 us per
+// launch at 32 Ki prompts, DRAM and issue slots both under 15 % busy).  Here a warp takes ONE prompt: the 32 lanes probe the
+// round's 32 keys at once (one memory round trip for the whole chunk), a ballot finds the first miss, and the blocks before it
+// are scored in order with lane q owning pod q (<= 10 pods); runs of blocks whose slot holds the same pods and tiers are runs of
+// in-order additions of the same addend.  ~700 issue slots per prompt-round instead of ~1/32 of a lockstep warp's: worth it
+// while the batch cannot fill the machine (kvidx.cu: rounds_warp_max).  Same arithmetic in the same order as every other path.
+// The 8 warps of a CTA run in lock step over 8 consecutive list slots so that the survivors are appended with one atomic per CTA
+// iteration, in list order.  Keys are prompt-major (hash_round_kernel<., true>).
+struct WarpWalkSmem { uint32_t p[kProbeThreads / 32]; unsigned int base; };
+__global__ void __launch_bounds__(kProbeThreads, 4)
+probe_round_warp_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round) {
+    __shared__ WarpWalkSmem sm;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr unsigned int WPC = kProbeThreads / 32;
+    const unsigned int n_act = rb.n_act[cur];
+    const uint64_t l2pol = l2_policy_stream();
+    const bool peer = t.shard_bits != 0;
+    for (unsigned int i0 = blockIdx.x * WPC; i0 < n_act; i0 += gridDim.x * WPC) {
+        const unsigned int i = i0 + wid;
+        const bool have = i < n_act;
+        uint32_t p = 0, meta = 0;
+        if (have) { p = rb.act[cur][i]; meta = rb.nbr[i]; }
+        const int nb = (int)(meta & 63u);
+        const bool has_more = (meta >> 8) & 1u;
+        const uint32_t mdl = (have && a.model) ? a.model[p] : a.model0;
+        uint64_t key = 0;
+        if (lane < nb) key = rb.keys[(size_t)i * kRoundBlocks + lane];
+        // walk state: lane q < k owns pod q
+        uint32_t k = 0, alive = 0, mypod = 0xffffffffu, mybt = 0xffu;
+        double mysc = 0.0;
+        uint32_t pv0 = 0, pv1 = 0, pv2 = 0, pv3 = 0, pv4 = 0, pvc = 0xffffffffu;
+        if (round > 0 && have) {
+            const PromptState& ps = rb.pst[p];
+            k = ps.k; alive = ps.alive;
+            pv0 = ps.pat[0]; pv1 = ps.pat[1]; pv2 = ps.pat[2]; pv3 = ps.pat[3]; pv4 = ps.pat[4]; pvc = ps.pat[5];
+            if ((uint32_t)lane < k) { mysc = ps.sc[lane]; mypod = ps.pod[lane]; mybt = ps.bt[lane]; }
+        }
+        // probe: lane j looks up block j's key
+        uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0, cnt = 0;
+        bool hit = false;
+        if (lane < nb) {
+            const uint64_t hm = home_of(key, mdl);
+            const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
+            uint64_t slot = hm & t.req_mask & ~1ull;
+            const bool remote = base != t.req;                  // a peer's shard: home slot first, its neighbour only if needed
+            for (;;) {
+                uint4 A0, B0, A1, B1;
+                ld_slot(base + slot, peer, A0, B0);
+                if (!remote) ld_slot(base + slot + 1, peer, A1, B1);
+                uint4 A = A0, B = B0;
+                hit = slot_matches(A, B, key, mdl);
+                bool stop = hit || meta_state(B.w) == kStateEmpty;
+                if (!stop) {
+                    if (remote) ld_slot(base + slot + 1, peer, A1, B1);
+                    A = A1; B = B1; hit = slot_matches(A, B, key, mdl); stop = hit || meta_state(B.w) == kStateEmpty;
+                }
+                if (hit) { e0 = A.z; e1 = A.w; e2 = B.x; e3 = B.y; e4 = B.z; cnt = meta_count(B.w); }
+                if (stop) break;
+                slot = (slot + 2) & t.req_mask;                 // rare: displaced past the home pair
+            }
+        }
+        const uint32_t hm_ = __ballot_sync(0xffffffffu, hit);
+        const int nhit = hm_ == 0xffffffffu ? 32 : __ffs(~hm_) - 1;   // consecutive hits from block 0 (lanes >= nb never hit)
+        bool done = nb == 0;
+        uint32_t samemask;                                      // block j's slot holds the same pods and tiers as block j-1's
+        {
+            const uint32_t u0 = __shfl_up_sync(0xffffffffu, e0, 1), u1 = __shfl_up_sync(0xffffffffu, e1, 1), u2 = __shfl_up_sync(0xffffffffu, e2, 1),
+                           u3 = __shfl_up_sync(0xffffffffu, e3, 1), u4 = __shfl_up_sync(0xffffffffu, e4, 1), uc = __shfl_up_sync(0xffffffffu, cnt, 1);
+            const bool sm_ = lane > 0 ? (((u0 ^ e0) | (u1 ^ e1) | (u2 ^ e2) | (u3 ^ e3) | (u4 ^ e4) | (uc ^ cnt)) == 0u)
+                                      : (round > 0 && ((pv0 ^ e0) | (pv1 ^ e1) | (pv2 ^ e2) | (pv3 ^ e3) | (pv4 ^ e4) | (pvc ^ cnt)) == 0u);
+            samemask = __ballot_sync(0xffffffffu, sm_ && lane < nhit);
+        }
+        int j = 0;
+        while (j < nhit && !done) {
+            if ((samemask >> j) & 1u) {
+                const uint32_t rest = ~(samemask >> j);
+                const int run = min(rest ? __ffs(rest) - 1 : 32, nhit - j);           // >= 1
+                if ((alive >> lane) & 1u) {
+                    const double add = mybt == 0xffu ? 0.0 : t.weight[mybt & 15u];
+                    for (int u = 0; u < run; ++u) mysc = __dadd_rn(mysc, add);
+                }
+                j += run;
+                continue;
+            }
+            const uint32_t w0 = __shfl_sync(0xffffffffu, e0, j), w1 = __shfl_sync(0xffffffffu, e1, j), w2 = __shfl_sync(0xffffffffu, e2, j),
+                           w3 = __shfl_sync(0xffffffffu, e3, j), w4 = __shfl_sync(0xffffffffu, e4, j), c = __shfl_sync(0xffffffffu, cnt, j);
+            if (round == 0 && j == 0) {
+                // activePods := pods of block 0 (after the filter), in entry order; score = max weight   (kvblock_scorer.go:118-128)
+                const uint64_t* frow = filter_row(a.filter, p, t.filter_words);
+                k = 0;
+                for (uint32_t e = 0; e < c; ++e) {
+                    const uint32_t pt = ent_of(w0, w1, w2, w3, w4, (int)e), pd = pt >> 4;
+                    if (frow && !filter_has(frow, pd)) continue;
+                    const double wt = t.weight[pt & 15u];
+                    const uint32_t own = __ballot_sync(0xffffffffu, (uint32_t)lane < k && mypod == pd);
+                    const int q = own ? __ffs(own) - 1 : (int)k;
+                    if (!own) { if (lane == q) { mypod = pd; mysc = 0.0; mybt = 0xffu; } ++k; }
+                    if (lane == q && wt > mysc) { mysc = wt; mybt = pt & 15u; }
+                }
+                alive = (1u << k) - 1u;
+            } else {
+                // activePods &= pods(block); score[p] += max weight, in block order   (kvblock_scorer.go:130-147)
+                bool present = false; double mx = 0.0; uint32_t bt = 0xffu;
+                if ((alive >> lane) & 1u) {
+                    for (uint32_t e = 0; e < c; ++e) {
+                        const uint32_t pt = ent_of(w0, w1, w2, w3, w4, (int)e);
+                        if ((pt >> 4) == mypod) { present = true; const double wt = t.weight[pt & 15u]; if (wt > mx) { mx = wt; bt = pt & 15u; } }
+                    }
+                    if (present) { mysc = __dadd_rn(mysc, mx); mybt = bt; }
+                }
+                alive = __ballot_sync(0xffffffffu, present);
+            }
+            if (!alive) done = true;
+            ++j;
+        }
+        if (j > 0) {                                            // pattern of the last scored block, for the next round's first comparison
+            const int lj = j - 1;
+            pv0 = __shfl_sync(0xffffffffu, e0, lj); pv1 = __shfl_sync(0xffffffffu, e1, lj); pv2 = __shfl_sync(0xffffffffu, e2, lj);
+            pv3 = __shfl_sync(0xffffffffu, e3, lj); pv4 = __shfl_sync(0xffffffffu, e4, lj); pvc = __shfl_sync(0xffffffffu, cnt, lj);
+        }
+        if (nhit < nb) done = true;                             // a block of the round is not in the index
+        const bool more = have && !done && has_more;
+        // survivors of the CTA's 8 slots, in slot order
+        if (lane == 0) sm.p[wid] = more ? p : 0xffffffffu;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int c = 0;
+            for (unsigned int w = 0; w < WPC; ++w) c += sm.p[w] != 0xffffffffu;
+            sm.base = c ? atomicAdd(&rb.n_act[cur ^ 1], c) : 0u;
+        }
+        __syncthreads();
+        if (more) {
+            unsigned int rank = 0;
+            for (int w = 0; w < wid; ++w) rank += sm.p[w] != 0xffffffffu;
+            PromptState& ps = rb.pst[p];
+            if ((uint32_t)lane < k) { ps.sc[lane] = mysc; ps.pod[lane] = (uint16_t)mypod; ps.bt[lane] = (uint8_t)mybt; }
+            if (lane == 0) {
+                rb.act[cur ^ 1][sm.base + rank] = p;
+                ps.k = (uint8_t)k; ps.alive = (uint16_t)alive;
+                ps.pat[0] = pv0; ps.pat[1] = pv1; ps.pat[2] = pv2; ps.pat[3] = pv3; ps.pat[4] = pv4; ps.pat[5] = pvc;
+            }
+        } else if (have) {
+            if (a.dense) {
+                double* row = a.dense + (long long)p * t.max_pods;
+                const uint32_t P = t.max_pods;
+                if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
+                    for (uint32_t c2 = lane * 2; c2 < P; c2 += 64) st_stream_f64x2(row + c2, -1.0, -1.0, l2pol);
+                } else {
+                    for (uint32_t c2 = lane; c2 < P; c2 += 32) row[c2] = -1.0;
+                }
+                __syncwarp();
+                if ((uint32_t)lane < k && mypod < P) row[mypod] = mysc;
+            }
+            if (a.sp_cnt) {
+                if ((uint32_t)lane < k) { a.sp_pods[(long long)p * kMaxEnt + lane] = (uint16_t)mypod; a.sp_scores[(long long)p * kMaxEnt + lane] = mysc; }
+                if (lane == 0) a.sp_cnt[p] = (uint8_t)k;
+            }
+            if (a.has_keys && lane == 0) a.has_keys[p] = (round > 0) || nb > 0;
+        }
+        __syncthreads();                                        // sm.p / sm.base are rewritten by the next iteration
     }
 }
 
@@ -359,7 +534,9 @@ __global__ void rounds_init_kernel(const ScoreArgs a, uint32_t block_size, unsig
 }
 
 inline int rounds_init() {
-    if (cudaFuncSetAttribute(hash_round_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(hash_round_kernel<16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(hash_round_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(hash_round_kernel<16, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(probe_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)) != cudaSuccess) return -1;
     return 0;
 }

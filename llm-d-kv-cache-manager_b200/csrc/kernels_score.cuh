@@ -129,6 +129,7 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
     using SM = ScoreSmem<BS>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint64_t l2pol = l2_policy_stream();
     typename SM::Warp& W = sm.w[wid];
     if (threadIdx.x < 16) sm.weight[threadIdx.x] = t.weight[threadIdx.x];
     __syncthreads();
@@ -165,7 +166,7 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
                     double* row = a.dense + ppi * (long long)t.max_pods;
                     const uint32_t P = t.max_pods;
                     if ((P & 1u) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15u) == 0)) {
-                        for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2_policy_stream());
+                        for (uint32_t c = lane * 2; c < P; c += 64) st_stream_f64x2(row + c, -1.0, -1.0, l2pol);
                     } else {
                         for (uint32_t c = lane; c < P; c += 32) row[c] = -1.0;
                     }
@@ -218,7 +219,7 @@ score_kernel_tuned(const TableView t, const ScoreArgs a) {
         for (int r = 0; r < 4; ++r) {                           // 8 prompts x 64 B per instruction
             const int p = 8 * r + (lane >> 2);
             const unsigned long long sp = __shfl_sync(0xffffffffu, srcv, p);
-            if (sp && !(KVX_ABLATE & 4)) cp_async_16_stream(smem_addr(&W.tok[s][p * SM::kRow + (lane & 3) * 16]), reinterpret_cast<const char*>(sp) + (lane & 3) * 16, l2_policy_stream());
+            if (sp && !(KVX_ABLATE & 4)) cp_async_16_stream(smem_addr(&W.tok[s][p * SM::kRow + (lane & 3) * 16]), reinterpret_cast<const char*>(sp) + (lane & 3) * 16, l2pol);
         }
         cp_async_commit();
         if (issue && !aligned) {                                // unaligned prompt start: this lane copies its own block

@@ -148,7 +148,8 @@ struct kvidx {
     int64_t zerocopy_max = 32;     // host-buffer calls up to this many prompts skip the copy engine (tokens read from pinned host memory)
     int group_tma = 0;             // class pipeline: token chunks by TMA bulk copy instead of cp.async (measured: 2 % slower per step)
     struct SubmitQueue* queue = nullptr;   // coalesces concurrent host-buffer Score() callers (submit.cuh)
-    int64_t rounds_min = 32768;    // batches at least this large use the round pipeline
+    int64_t rounds_min = 4096;     // batches at least this large use the round pipeline (measured: warp-per-prompt rounds beat the fused
+                                   // kernel from 4096 prompts, profiles/r2_medium_batch_ab.txt)
     int64_t classes_min = 393216;  // ... and at least this large, the prefix-class round pipeline
     double classes_min_sharing = 0.85;   // ... if at least this fraction of the batch follows a representative in round 0
     DevBuf r_act0, r_act1, r_cnt, r_hstate, r_keys, r_pst, r_nbr, r_fp, r_sort, r_role, r_hl, r_map, r_src, r_fate, r_anch, r_snap, r_rec;
@@ -165,6 +166,8 @@ struct kvidx {
     // latency-bound kernels (G2, H, P, R) run beside it on their own streams (otherwise the parts drift into lock step: all in
     // G sharing the bandwidth, then all in the short kernels with DRAM idle -- scripts/timeline.py)
     int group_serial = 2, group_serial_grid = 2;
+    int rounds_warp = 1, rounds_warp_stages = 3; int64_t rounds_warp_max = 57344;       // per-prompt rounds: kernel P warp per prompt up to this many prompts
+                                   // (measured crossover with the lane-per-prompt kernel P between 49152 and 65536)
     int group_ctas = 0;            // > 0: CTAs of one part's kernel G (all parts' G CTAs resident at once: nothing queues behind them)
     int hash_prefetch = 0;         // kernel H pulls its chunks towards L2 before the chain starts (1; 2: evict_last)
     int small_cta = 256;           // threads per CTA of the short kernels (G2, H, P, R): small CTAs fit into what kernel G's CTAs leave of an SM
@@ -485,6 +488,7 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
                         const uint32_t* d_model, uint32_t model0, const uint64_t* d_filter, const ScoreOut& o, cudaStream_t st,
                         int64_t max_blocks) {
     const bool spec = x->rounds_spec && n <= x->rounds_spec_max;
+    const bool warp_walk = !spec && x->rounds_warp && n <= x->rounds_warp_max;      // kernel P: warp per prompt (batch too small to fill the machine lane per prompt)
     CK(x->r_act0.need((size_t)n * 4)); CK(x->r_act1.need((size_t)n * 4)); CK(x->r_cnt.need(64));
     CK(x->r_hstate.need((size_t)n * 8)); CK(x->r_keys.need((size_t)n * plain::kRoundBlocks * 8 * (spec ? 2 : 1))); CK(x->r_pst.need((size_t)n * sizeof(plain::PromptState)));
     CK(x->r_nbr.need((size_t)n * 4 * (spec ? 2 : 1)));
@@ -499,7 +503,7 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
         rb[hlf].act[0] = x->r_act0.as<uint32_t>() + off; rb[hlf].act[1] = x->r_act1.as<uint32_t>() + off;
         rb[hlf].n_act = cnt + 2 * hlf;
         rb[hlf].hstate = x->r_hstate.as<uint64_t>(); rb[hlf].pst = x->r_pst.as<plain::PromptState>();
-        rb[hlf].keys = x->r_keys.as<uint64_t>() + off; rb[hlf].nbr = x->r_nbr.as<uint32_t>() + off;
+        rb[hlf].keys = x->r_keys.as<uint64_t>() + (warp_walk ? off * plain::kRoundBlocks : off); rb[hlf].nbr = x->r_nbr.as<uint32_t>() + off;      // prompt-major keys: a half's rows are contiguous
         rb[hlf].spec = spec ? 1 : 0;
         if (spec) { rb[hlf].prev[0] = x->r_hl.as<uint32_t>() + off; rb[hlf].prev[1] = x->r_hl.as<uint32_t>() + n + off; }
     }
@@ -537,10 +541,19 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
             for (int hlf = 0; hlf < nh; ++hlf) {
                 const int64_t m = hlf ? nB : nA;
                 const unsigned hgrid = (unsigned)std::min<int64_t>((m + plain::kHashThreads - 1) / plain::kHashThreads, (int64_t)x->sm_count * per_sm_h);
-                plain::hash_round_kernel<16><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+                if (warp_walk && x->rounds_warp_stages == 3) {      // 128-thread CTAs, three stages: 55 KB, four CTAs per SM
+                    const unsigned hg = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)x->sm_count * 4);
+                    plain::hash_round_kernel<16, true, 3><<<hg, 128, sizeof(plain::HashSmem<16>) / 8 / 2 * 3 * 4, strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+                } else if (warp_walk) plain::hash_round_kernel<16, true, 2><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+                else plain::hash_round_kernel<16, false, 2><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
             }
             for (int hlf = 0; hlf < nh; ++hlf) {
                 const int64_t m = hlf ? nB : nA;
+                if (warp_walk) {      // warp per prompt: 8 prompts per CTA iteration
+                    const unsigned pgrid = (unsigned)std::min<int64_t>((m + 7) / 8, (int64_t)x->sm_count * 8);
+                    plain::probe_round_warp_kernel<<<pgrid, plain::kProbeThreads, 0, strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+                    continue;
+                }
                 const unsigned pgrid = (unsigned)std::min<int64_t>((m + plain::kProbeThreads - 1) / plain::kProbeThreads, (int64_t)x->sm_count * per_sm_p);
                 plain::probe_round_kernel<<<pgrid, plain::kProbeThreads, sizeof(plain::WalkSmem), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
             }
@@ -562,7 +575,7 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
             rr.keys += (size_t)cur * (size_t)n * plain::kRoundBlocks; rr.nbr += (size_t)cur * (size_t)n;
             if (r >= 2) CK(cudaStreamWaitEvent(sH[hlf], x->ev_spec_p[hlf][cur], 0));                 // P(r-2) built the list H(r) runs over ... (r-1)&1 == cur^1; see below
             const unsigned hgrid = (unsigned)std::min<int64_t>((m + plain::kHashThreads - 1) / plain::kHashThreads, (int64_t)x->sm_count * per_sm_h);
-            plain::hash_round_kernel<16><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), sH[hlf]>>>(x->tv, a, rr, cur, (int)r);
+            plain::hash_round_kernel<16, false, 2><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), sH[hlf]>>>(x->tv, a, rr, cur, (int)r);
             CK(cudaEventRecord(x->ev_spec_h[hlf][cur], sH[hlf]));
             CK(cudaStreamWaitEvent(sP[hlf], x->ev_spec_h[hlf][cur], 0));
             CK(cudaMemsetAsync(rb[hlf].n_act + (cur ^ 1), 0, sizeof(unsigned int), sP[hlf]));      // the list P(r) appends to starts empty
@@ -1117,6 +1130,9 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
     if (const char* k = getenv("KVIDX_GROUP_SERIAL")) x->group_serial = atoi(k);
     if (const char* k = getenv("KVIDX_HASH_PREFETCH")) x->hash_prefetch = atoi(k);
     if (const char* k = getenv("KVIDX_GROUP_CTAS")) x->group_ctas = atoi(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_WARP")) x->rounds_warp = atoi(k) != 0;
+    if (const char* k = getenv("KVIDX_ROUNDS_WARP_MAX")) x->rounds_warp_max = atoll(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_WARP_STAGES")) x->rounds_warp_stages = atoi(k) == 3 ? 3 : 2;
     if (const char* k = getenv("KVIDX_SMALL_CTA")) { const int v = atoi(k); if (v == 32 || v == 64 || v == 128 || v == 256) x->small_cta = v; }
     if (const char* k = getenv("KVIDX_GROUP_SERIAL_GRID")) x->group_serial_grid = std::max(1, atoi(k));
     if (const char* k = getenv("KVIDX_ROUNDS_DEDUP")) x->rounds_dedup = atoi(k);

@@ -332,9 +332,13 @@ def _select_path(monkeypatch, path):
         monkeypatch.setenv("KVIDX_GROUP_TMA", "1")
     elif var == "nospec":                    # per-prompt rounds without the speculative hash / walk overlap
         monkeypatch.setenv("KVIDX_ROUNDS_SPEC", "0")
+    elif var == "lane":                      # per-prompt rounds with the lane-per-prompt kernel P (what batches above 131 072 take)
+        monkeypatch.setenv("KVIDX_ROUNDS_WARP", "0")
+    elif var == "spec":                      # ... with the speculative hash / walk overlap (off by default)
+        monkeypatch.setenv("KVIDX_ROUNDS_SPEC", "1")
 
 
-ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "rounds-nospec", "rounds2-nospec", "classes", "classes2", "classes8", "classes-nosort",
+ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "rounds-lane", "rounds2-lane", "rounds2-spec", "rounds-nospec", "rounds2-nospec", "classes", "classes2", "classes8", "classes-nosort",
                "classes-nodedup", "classes-whole", "classes4-whole", "classes-tma", "classes8-tma", "auto"]
 PATHS = ["v1", "fused", "coop"] + ROUND_PATHS
 
