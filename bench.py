@@ -153,8 +153,16 @@ def measured_peak():
 
 
 def ncu_traffic():
-    """DRAM bytes (read+write) per prompt of one Score() step, summed over its kernels, from the committed ncu
-    capture (profiles/score_step_traffic.json); None if no capture is committed."""
+    """DRAM bytes (read+write) per prompt of one default Score() step from the committed ncu captures: the range profile of the
+    whole step (profiles/r2_step_range_profile.json, `ncu --replay-mode range --set full`, its kernels as one unit), else the sum
+    over the per-kernel launch list (profiles/score_step_traffic.json); None if neither is committed."""
+    try:
+        m = json.load(open(os.path.join(ROOT, "profiles", "r2_step_range_profile.json")))["metrics"]
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = sum(float(m[k]["value"]) * unit[m[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        return tot / 1048576.0
+    except Exception:
+        pass
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "score_step_traffic.json")))["dram_bytes_per_prompt"]
     except Exception:
@@ -572,11 +580,11 @@ def run_ours(args):
             "traffic": None if traffic is None else traffic * Q,
             "peak_source": peak_src, "algorithmic_bytes_per_prompt_mean": float(A.mean()),
             "algorithmic_bytes_per_launch": float(A.sum()), "kernel_ms": float(step_ms.mean()),
-            "kernel": "one step = prefix sort + rounds x parts x (group_round [TMA chunks], group_lists, hash_round, walk_round, finish_round); "
+            "kernel": "one step = prefix sort + rounds x parts x (group_round [cp.async token chunks], group_lists, hash_round, walk_round, finish_round), kernel G on low-priority streams; "
                       "achieved = step's algorithmic bytes / step GPU time (CUDA events around all of its launches), i.e. a lower bound for "
                       "every kernel in it; per-kernel ncu summaries under profiles/",
-            "note": "traffic = DRAM bytes of one step from the committed ncu capture (profiles/score_step_traffic.json), default single-GPU "
-                    "configuration only; null for any other configuration"}
+            "note": "traffic = DRAM bytes of one step from the committed ncu range profile of the whole step (profiles/r2_step_range_profile.json; "
+                    "per kernel: profiles/score_step_traffic.json), default single-GPU configuration only; null for any other configuration"}
 
     # ---- e2e: host pinned buffers through the C ABI (H2D + kernels + D2H inside the timed region) ----
     #   headline e2e: kvidx_score_batch_sparse -- the reference's result shape (a map of <= 10 pods per prompt, indexer.go:134)

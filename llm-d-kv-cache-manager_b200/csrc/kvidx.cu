@@ -455,8 +455,9 @@ int launch_score_rounds(kvidx* x, const uint32_t* d_tok, const int64_t* d_off, i
         for (int q = 0; q < np; ++q) {
             const int64_t m = psz[q];
             if (m <= 0) continue;
-            const unsigned hgrid = (unsigned)std::min<int64_t>((m + T - 1) / T, (int64_t)x->sm_count * kf * (np == 1 ? 4 : x->rounds_grid[2]));
-            hash_round_kernel<16><<<hgrid, T, sizeof(HashSmem<16>) / (kHashThreads / 32) * W, sS[q]>>>(x->tv, a, rb[q], cur, (int)r, x->hash_prefetch);
+            const int TH = std::min(T, kHashThreads);
+            const unsigned hgrid = (unsigned)std::min<int64_t>((m + TH - 1) / TH, (int64_t)x->sm_count * (256 / TH) * (np == 1 ? 4 : x->rounds_grid[2]));
+            hash_round_kernel<16><<<hgrid, TH, sizeof(HashSmem<16>) / (kHashThreads / 32) * (TH / 32), sS[q]>>>(x->tv, a, rb[q], cur, (int)r, x->hash_prefetch);
             const unsigned wgrid = (unsigned)std::min<int64_t>((m + W - 1) / W, (int64_t)x->sm_count * kf * (np == 1 ? 8 : x->rounds_grid[3]));
             walk_round_kernel<<<wgrid, T, 0, sS[q]>>>(x->tv, a, rb[q], cur, (int)r);
             const unsigned rgrid = (unsigned)std::min<int64_t>((m + T - 1) / T, (int64_t)x->sm_count * kf * (np <= 2 ? 8 : x->rounds_grid[4]));
