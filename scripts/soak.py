@@ -16,6 +16,9 @@ def one(seed):
     cfg = [("classes", "1"), ("classes", "2"), ("classes", "8"), ("rounds", "2"), ("classes", "4"), ("coop", "1"), ("coop", "1"), ("fused", "1")][int(rng.integers(0, 8))]
     os.environ["KVIDX_GROUP_TMA"] = str(int(rng.integers(0, 2)))
     os.environ["KVIDX_ROUNDS_SPEC"] = str(int(rng.integers(0, 2)))
+    os.environ["KVIDX_ROUNDS_WARP"] = str(int(rng.integers(0, 2)))           # per-prompt rounds: warp- / lane-per-prompt walk kernel
+    os.environ["KVIDX_GROUP_SERIAL"] = str(int(rng.integers(0, 3)))         # where kernel G runs (part stream / one stream / low-priority streams)
+    os.environ["KVIDX_SMALL_CTA"] = str(int(rng.choice([64, 128, 256])))
     os.environ["KVIDX_ZEROCOPY_MAX"] = str(int(rng.choice([0, 32])))
     os.environ["KVIDX_SCORE_PATH"] = cfg[0]
     os.environ["KVIDX_ROUNDS_OVERLAP_MIN"] = "64"
