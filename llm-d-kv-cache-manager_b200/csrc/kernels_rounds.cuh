@@ -436,22 +436,18 @@ group_lists_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, con
         unsigned int b0 = 0, b1 = 0, b2 = 0;
         if (lane == 0) {
             if (m0) b0 = atomicAdd(&rb.n_hl[0], (unsigned int)__popc(m0));
-            if (m0 | m1) b1 = atomicAdd(&rb.n_hl[1], (unsigned int)__popc(m0 | m1));
+            if (m1) b1 = atomicAdd(&rb.n_hl[1], (unsigned int)__popc(m1));
             if (m2) b2 = atomicAdd(&rb.n_hl[2], (unsigned int)__popc(m2));
         }
         b0 = __shfl_sync(0xffffffffu, b0, 0); b1 = __shfl_sync(0xffffffffu, b1, 0); b2 = __shfl_sync(0xffffffffu, b2, 0);
         const uint32_t below = (1u << lane) - 1u;
-        // the MEMBER list (representatives and followers together, in the order of the live list): kernel R builds the next live
-        // list from it, so a class's representative stays next to the followers it had in this tile and the next round's kernel G
-        // finds them as one run (appended as "all representatives, then all followers" every follower run had to find its class
-        // again through the election: a 4 KB re-read each)
-        if (kind == 0 || kind == 1) rb.fl[b1 + __popc((m0 | m1) & below)] = i;
         if (kind == 0) {
             const unsigned int ap = b0 + __popc(m0 & below);
             const uint32_t p = rb.act[cur][i];
             rb.hl[ap] = i; rb.apos[i] = ap;
             rb.rec[ap] = make_uint4(p, i, rb.nbr[i], round > 0 ? rb.src[p] : p);
-        } else if (kind == 2) {
+        } else if (kind == 1) rb.fl[b1 + __popc(m1 & below)] = i;
+        else if (kind == 2) {
             const unsigned int dp = b2 + __popc(m2 & below);
             rb.dl[dp] = i;
             rb.drec[dp] = make_uint4(rb.act[cur][i], target, ((uint32_t)dshare << 16) | rb.nbr[i], rb.act[cur][target]);
@@ -753,7 +749,7 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
 }
 
 // ---- kernel R: followers take their representative's outcome --------------------------------------------------
-// Lane per MEMBER of a class (representative or follower, in live-list order).  Representative continues: so does the follower, with the representative's chain state, and its
+// Lane per follower.  Representative continues: so does the follower, with the representative's chain state, and its
 // walk state stays where the representative left it (src).  Representative finished: same pods, same scores -- the warp
 // writes the follower's result from the representative's final state.
 __device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round,
@@ -763,20 +759,31 @@ __device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArg
         uint32_t* f4 = reinterpret_cast<uint32_t*>(rb.need_snap);
         for (size_t x = bid * (size_t)blockDim.x + threadIdx.x; x < rb.part_size / 4; x += (size_t)nbl * blockDim.x) f4[x] = 0u;
     }
-    const unsigned int n_fl = rb.n_hl[1];                     // members: representatives and followers, in live-list order
+    {                                                          // representatives that continue (walk_round_kernel leaves the list to us)
+        const unsigned int n_a = rb.n_hl[0];
+        const unsigned int tw = nbl * (blockDim.x / 32);
+        for (unsigned int w = bid * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_a; w += tw) {
+            const unsigned int i = w * 32u + lane;
+            const unsigned int li = i < n_a ? rb.hl[i] : 0u;
+            const bool more = i < n_a && rb.fate[li] == kFateMore;
+            const uint32_t mm = __ballot_sync(0xffffffffu, more);
+            if (!mm) continue;
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&rb.n_act[cur ^ 1], (unsigned int)__popc(mm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (more) { const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u)); const uint32_t pp = rb.act[cur][li]; rb.act[cur ^ 1][ns] = pp; rb.lslot[pp] = ns; }
+        }
+    }
+    const unsigned int n_fl = rb.n_hl[1];
     const PromptState* pst_cur = rb.pst[round & 1];
     const unsigned int total_warps = nbl * (blockDim.x / 32);
     for (unsigned int w = bid * (blockDim.x / 32) + (threadIdx.x >> 5); w * 32u < n_fl; w += total_warps) {
         const unsigned int f = w * 32u + lane;
         const bool have = f < n_fl;
         uint32_t p = 0, pl = 0; uint8_t ft = 0;
-        bool isrep = false;
         if (have) {
-            const unsigned int li = rb.fl[f];
-            unsigned int lj = rb.role[li];
-            isrep = lj == kRoleSelf;
-            if (isrep) lj = li;
-            p = rb.act[cur][li]; pl = isrep ? p : rb.act[cur][lj]; ft = rb.fate[lj];
+            const unsigned int li = rb.fl[f], lj = rb.role[li];
+            p = rb.act[cur][li]; pl = rb.act[cur][lj]; ft = rb.fate[lj];
         }
         const bool more = have && ft == kFateMore;
         const uint32_t mm = __ballot_sync(0xffffffffu, more);
@@ -786,13 +793,11 @@ __device__ __forceinline__ void resolve_round(const TableView& t, const ScoreArg
             base = __shfl_sync(0xffffffffu, base, 0);
             if (more) {
                 { const unsigned int ns = base + __popc(mm & ((1u << lane) - 1u)); rb.act[cur ^ 1][ns] = p; rb.lslot[p] = ns; }
-                if (!isrep) {                                   // (a representative's own state was written by kernel P)
-                    rb.src[p] = pl;
-                    rb.hstate[p] = rb.hstate[pl]; rb.pos[p] = rb.pos[pl];
-                }
+                rb.src[p] = pl;
+                rb.hstate[p] = rb.hstate[pl]; rb.pos[p] = rb.pos[pl];
             }
         }
-        uint32_t dm = __ballot_sync(0xffffffffu, have && !more && !isrep);      // (a finished representative's row was written by kernel P)
+        uint32_t dm = __ballot_sync(0xffffffffu, have && !more);
         while (dm) {
             const int l = __ffs(dm) - 1; dm &= dm - 1;
             const uint32_t pp = __shfl_sync(0xffffffffu, p, l);
