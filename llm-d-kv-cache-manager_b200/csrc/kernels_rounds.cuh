@@ -614,7 +614,7 @@ walk_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, cons
             // A local probe fetches the aligned slot PAIR (one 64-byte DRAM access).  On a peer GPU's shard every byte crosses
             // NVLink, and at load <= 0.25 the home slot alone decides ~9 probes out of 10: fetch it first, its neighbour only
             // if needed (halves the NVLink bytes of a sharded step, profiles/r2_sharded_nvlink.json).
-            const bool remote = base != t.req;
+            const bool remote = base != t.req && !t.peer_pair;
             for (;;) {
                 uint4 A0, B0, A1, B1;
                 ld_slot(base + slot, peer, A0, B0);
@@ -902,7 +902,7 @@ __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs
                     const uint64_t hm = home_of(hk, mdl);
                     const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
                     uint64_t slot = hm & t.req_mask & ~1ull;
-                    const bool remote = base != t.req;                  // a peer's shard: home slot first, its neighbour only if needed
+                    const bool remote = base != t.req && !t.peer_pair;                  // a peer's shard: home slot first, its neighbour only if needed
                     uint4 A0, B0, A1, B1;
                     ld_slot(base + slot, peer, A0, B0);
                     if (!remote) ld_slot(base + slot + 1, peer, A1, B1);

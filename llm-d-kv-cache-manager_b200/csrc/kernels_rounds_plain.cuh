@@ -384,7 +384,7 @@ probe_round_warp_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb
             const uint64_t hm = home_of(key, mdl);
             const ReqSlot* base = t.req_peer[shard_of(hm, t.shard_bits)];
             uint64_t slot = hm & t.req_mask & ~1ull;
-            const bool remote = base != t.req;                  // a peer's shard: home slot first, its neighbour only if needed
+            const bool remote = base != t.req && !t.peer_pair;                  // a peer's shard: home slot first, its neighbour only if needed
             for (;;) {
                 uint4 A0, B0, A1, B1;
                 ld_slot(base + slot, peer, A0, B0);

@@ -1130,6 +1130,7 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
     if (const char* k = getenv("KVIDX_ROUNDS_PARTS")) x->rounds_parts = atoi(k);
     if (const char* k = getenv("KVIDX_GROUP_SERIAL")) x->group_serial = atoi(k);
     if (const char* k = getenv("KVIDX_HASH_PREFETCH")) x->hash_prefetch = atoi(k);
+    if (const char* k = getenv("KVIDX_PEER_PAIR")) x->tv.peer_pair = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_GROUP_CTAS")) x->group_ctas = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_WARP")) x->rounds_warp = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_WARP_MAX")) x->rounds_warp_max = atoll(k);

@@ -99,6 +99,8 @@ struct TableView {
     EngSlot* eng_peer[8];
     Counters* cnt_peer[8];
     uint32_t shard_bits, shard_rank;
+    uint32_t peer_pair;              // 1: a probe of a peer's shard fetches the slot pair at once (64 B) like a local one; 0: the home slot
+                                     // first, its neighbour only if needed (half the NVLink bytes, a second dependent round trip for ~1 probe in 10)
 };
 
 #ifdef __CUDACC__
