@@ -128,7 +128,10 @@ __device__ __forceinline__ void chunk_load(const uint32_t* sp, int nw, int lane,
 #define KVIDX_GROUP_TILE 32
 #endif
 constexpr int kGroupTile = KVIDX_GROUP_TILE;   // live prompts a warp of kernel G takes at a time (their chunks stream through the warp one after the other)
-constexpr int kGroupRing = 4;            // chunk slots per warp: one being examined, two in flight, the anchor (deeper rings measured: slower)
+#ifndef KVIDX_GROUP_RING
+#define KVIDX_GROUP_RING 4
+#endif
+constexpr int kGroupRing = KVIDX_GROUP_RING;            // chunk slots per warp: one being examined, two in flight, the anchor (deeper rings measured: slower)
 struct GroupSmem {
     uint4 ring[kGroupThreads / 32][kGroupRing][4][32];                       // 64 KB
     unsigned long long bar[kGroupThreads / 32][kGroupRing];                  // TMA variant: one mbarrier per rotating slot
@@ -138,7 +141,7 @@ struct GroupSmem {
 // mbarrier (UBLKCP in SASS) instead of four 16-byte cp.async per lane (LDGSTS); chunks that do not start on a 16-byte
 // boundary are copied with plain loads in both variants.
 template <int BS, bool TMA>
-__global__ void __launch_bounds__(kGroupThreads, 3)
+__global__ void __launch_bounds__(kGroupThreads, kGroupRing <= 4 ? 3 : 2)
 group_round_kernel(const TableView t, const ScoreArgs a, const RoundBufs rb, const int cur, const int round, const int dedup) {
     static_assert(BS == 16 && kRoundBlocks == 32, "a chunk is 4 x 32 lanes x 16 bytes");
     extern __shared__ __align__(128) unsigned char smem_raw_g[];
@@ -842,7 +845,10 @@ __device__ __forceinline__ uint64_t hash_block16(uint64_t parent, const uint32_t
     }
     return f.end_block();
 }
-constexpr int kDetachBlocks = 3;          // blocks a partial follower walks alone inside the round before it is re-queued
+#ifndef KVIDX_DETACH_BLOCKS
+#define KVIDX_DETACH_BLOCKS 3
+#endif
+constexpr int kDetachBlocks = KVIDX_DETACH_BLOCKS;          // blocks a partial follower walks alone inside the round before it is re-queued
 struct DetachWarp { double sc[kMaxEnt][32]; uint16_t pod[kMaxEnt][32]; };     // per warp (dynamic shared memory: warps of the CTA x this)
 template <int BS>
 __device__ __forceinline__ void detach_round(const TableView& t, const ScoreArgs& a, const RoundBufs& rb, const int cur, const int round, const int trace, DetachWarp* smw,
