@@ -332,6 +332,13 @@ def _select_path(monkeypatch, path):
         monkeypatch.setenv("KVIDX_GROUP_TMA", "1")
     elif var == "nospec":                    # per-prompt rounds without the speculative hash / walk overlap
         monkeypatch.setenv("KVIDX_ROUNDS_SPEC", "0")
+    elif var == "serial0":                   # class pipeline: every kernel of a part on the part's stream
+        monkeypatch.setenv("KVIDX_GROUP_SERIAL", "0")
+    elif var == "serial1":                   # ... all parts' token-streaming kernels on ONE stream
+        monkeypatch.setenv("KVIDX_GROUP_SERIAL", "1")
+    elif var == "cta64":                     # ... short kernels with 64-thread CTAs, hash kernel pulling its chunks to L2 first
+        monkeypatch.setenv("KVIDX_SMALL_CTA", "64")
+        monkeypatch.setenv("KVIDX_HASH_PREFETCH", "1")
     elif var == "lane":                      # per-prompt rounds with the lane-per-prompt kernel P (what batches above 131 072 take)
         monkeypatch.setenv("KVIDX_ROUNDS_WARP", "0")
     elif var == "spec":                      # ... with the speculative hash / walk overlap (off by default)
@@ -339,7 +346,8 @@ def _select_path(monkeypatch, path):
 
 
 ROUND_PATHS = ["rounds", "rounds2", "rounds-nosort", "rounds-lane", "rounds2-lane", "rounds2-spec", "rounds-nospec", "rounds2-nospec", "classes", "classes2", "classes8", "classes-nosort",
-               "classes-nodedup", "classes-whole", "classes4-whole", "classes-tma", "classes8-tma", "auto"]
+               "classes-nodedup", "classes-whole", "classes4-whole", "classes-tma", "classes8-tma", "classes8-serial0", "classes8-serial1",
+               "classes4-cta64", "auto"]
 PATHS = ["v1", "fused", "coop"] + ROUND_PATHS
 
 
