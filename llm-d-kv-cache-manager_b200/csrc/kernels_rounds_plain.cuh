@@ -537,6 +537,7 @@ inline int rounds_init() {
     if (cudaFuncSetAttribute(hash_round_kernel<16, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(hash_round_kernel<16, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(hash_round_kernel<16, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(hash_round_kernel<16, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(HashSmem<16>)) != cudaSuccess) return -1;
     if (cudaFuncSetAttribute(probe_round_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WalkSmem)) != cudaSuccess) return -1;
     return 0;
 }

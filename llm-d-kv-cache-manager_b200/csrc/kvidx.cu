@@ -166,6 +166,7 @@ struct kvidx {
     // latency-bound kernels (G2, H, P, R) run beside it on their own streams (otherwise the parts drift into lock step: all in
     // G sharing the bandwidth, then all in the short kernels with DRAM idle -- scripts/timeline.py)
     int group_serial = 2, group_serial_grid = 2;
+    int rounds_lane_stages = 2; int64_t rounds_lane_stages_max = 1 << 30;      // lane-per-prompt rounds: stages of kernel H (experiment knob)
     int rounds_warp = 1, rounds_warp_stages = 3; int64_t rounds_warp_max = 57344;       // per-prompt rounds: kernel P warp per prompt up to this many prompts
                                    // (measured crossover with the lane-per-prompt kernel P between 49152 and 65536)
     int group_ctas = 0;            // > 0: CTAs of one part's kernel G (all parts' G CTAs resident at once: nothing queues behind them)
@@ -546,7 +547,10 @@ int launch_score_rounds_plain(kvidx* x, const uint32_t* d_tok, const int64_t* d_
                     const unsigned hg = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)x->sm_count * 4);
                     plain::hash_round_kernel<16, true, 3><<<hg, 128, sizeof(plain::HashSmem<16>) / 8 / 2 * 3 * 4, strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
                 } else if (warp_walk) plain::hash_round_kernel<16, true, 2><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
-                else plain::hash_round_kernel<16, false, 2><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+                else if (x->rounds_lane_stages == 3 && n <= x->rounds_lane_stages_max) {
+                    const unsigned hg = (unsigned)std::min<int64_t>((m + 127) / 128, (int64_t)x->sm_count * 4);
+                    plain::hash_round_kernel<16, false, 3><<<hg, 128, sizeof(plain::HashSmem<16>) / 8 / 2 * 3 * 4, strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
+                } else plain::hash_round_kernel<16, false, 2><<<hgrid, plain::kHashThreads, sizeof(plain::HashSmem<16>), strm[hlf]>>>(x->tv, a, rb[hlf], cur, (int)r);
             }
             for (int hlf = 0; hlf < nh; ++hlf) {
                 const int64_t m = hlf ? nB : nA;
@@ -1134,6 +1138,7 @@ int create_impl(const kvidx_config_t& c, kvidx* x) {
     if (const char* k = getenv("KVIDX_GROUP_CTAS")) x->group_ctas = atoi(k);
     if (const char* k = getenv("KVIDX_ROUNDS_WARP")) x->rounds_warp = atoi(k) != 0;
     if (const char* k = getenv("KVIDX_ROUNDS_WARP_MAX")) x->rounds_warp_max = atoll(k);
+    if (const char* k = getenv("KVIDX_ROUNDS_LANE_STAGES")) x->rounds_lane_stages = atoi(k) == 3 ? 3 : 2;
     if (const char* k = getenv("KVIDX_ROUNDS_WARP_STAGES")) x->rounds_warp_stages = atoi(k) == 3 ? 3 : 2;
     if (const char* k = getenv("KVIDX_SMALL_CTA")) { const int v = atoi(k); if (v == 32 || v == 64 || v == 128 || v == 256) x->small_cta = v; }
     if (const char* k = getenv("KVIDX_GROUP_SERIAL_GRID")) x->group_serial_grid = std::max(1, atoi(k));
